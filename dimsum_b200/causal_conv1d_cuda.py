@@ -1,0 +1,115 @@
+"""Drop-in for the reference's pybind module `causal_conv1d_cuda` (causal-conv1d/csrc/causal_conv1d.cpp:571-577).
+
+Same function names, argument order, checks and return values.  `causal_conv1d_fwd_cond` keeps the reference's
+observable contract: the conditioning tensor is only the output buffer and is overwritten
+(causal_conv1d.cpp:326).  The channel-last layout and the decode-time `causal_conv1d_update` are outside this
+hot path and raise NotImplementedError (no fallback).
+"""
+import torch
+
+from . import _lib
+
+_DT = {torch.float32: _lib.DTYPE_F32, torch.float16: _lib.DTYPE_F16, torch.bfloat16: _lib.DTYPE_BF16}
+
+
+def _check(cond, msg):
+    if not cond:
+        raise RuntimeError(msg)
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _checks(x, weight, bias_):
+    _check(x.dtype in _DT, "causal_conv1d: input must be float32, float16 or bfloat16")
+    _check(weight.dtype in _DT, "causal_conv1d: weight must be float32, float16 or bfloat16")
+    _check(x.is_cuda and weight.is_cuda, "causal_conv1d: x and weight must be CUDA tensors")
+    _check(x.dim() == 3 and weight.dim() == 2, "causal_conv1d: x must be (batch, dim, seqlen), weight (dim, width)")
+    batch, dim, seqlen = x.shape
+    width = weight.shape[1]
+    _check(weight.shape[0] == dim, "causal_conv1d: weight shape mismatch")
+    _check(2 <= width <= 4, "causal_conv1d only supports width between 2 and 4")
+    if x.stride(2) != 1:
+        if x.stride(1) == 1:
+            raise NotImplementedError("causal_conv1d: channel-last layout is not implemented in the B200 kernels")
+        raise RuntimeError("causal_conv1d: x must have stride(2) == 1")
+    if bias_ is not None:
+        _check(bias_.dtype == weight.dtype and bias_.is_cuda and bias_.stride(-1) == 1 and tuple(bias_.shape) == (dim,),
+               "causal_conv1d: bias must be a contiguous (dim,) CUDA tensor of the weight dtype")
+    return batch, dim, seqlen, width
+
+
+def _fwd_into(x, weight, bias_, silu_activation, out, perm=None):
+    batch, dim, seqlen, width = _checks(x, weight, bias_)
+    with torch.cuda.device(x.device):
+        p = _lib.ConvFwdParams()
+        p.batch, p.dim, p.seqlen, p.width = batch, dim, seqlen, width
+        p.io_dtype, p.w_dtype, p.silu = _DT[x.dtype], _DT[weight.dtype], int(bool(silu_activation))
+        p.x_batch_stride, p.x_d_stride = x.stride(0), x.stride(1)
+        p.out_batch_stride, p.out_d_stride = out.stride(0), out.stride(1)
+        p.w_d_stride, p.w_width_stride = weight.stride(0), weight.stride(1)
+        p.x, p.weight, p.out = x.data_ptr(), weight.data_ptr(), out.data_ptr()
+        p.bias = bias_.data_ptr() if bias_ is not None else None
+        if perm is not None:
+            _check(perm.dtype == torch.int32 and perm.is_cuda and perm.is_contiguous() and perm.numel() == seqlen,
+                   "causal_conv1d: perm must be a contiguous int32 CUDA tensor of length seqlen")
+            p.perm = perm.data_ptr()
+        _lib.call("dimsum_causal_conv1d_fwd", p, _stream(x))
+    return out
+
+
+def causal_conv1d_fwd(x, weight, bias_, silu_activation, *, perm=None):
+    """causal_conv1d.cpp:221-281.  out = empty_like(x)."""
+    _checks(x, weight, bias_)
+    out = torch.empty(x.shape, device=x.device, dtype=x.dtype)
+    return _fwd_into(x, weight, bias_, silu_activation, out, perm)
+
+
+def causal_conv1d_fwd_cond(x, weight, bias_, silu_activation, init_x):
+    """causal_conv1d.cpp:283-347: `at::Tensor out = init_x;` -- writes the result into init_x and returns it."""
+    _checks(x, weight, bias_)
+    if init_x is None:
+        return causal_conv1d_fwd(x, weight, bias_, silu_activation)
+    _check(init_x.dtype == x.dtype and init_x.is_cuda and init_x.shape == x.shape and init_x.stride(2) == 1,
+           "causal_conv1d_fwd_cond: init_x must match x in dtype and shape")
+    return _fwd_into(x, weight, bias_, silu_activation, init_x)
+
+
+def causal_conv1d_bwd(x, weight, bias_, dout, dx_, silu_activation):
+    """causal_conv1d.cpp:349-427 -> [dx, dweight, dbias]."""
+    batch, dim, seqlen, width = _checks(x, weight, bias_)
+    _check(dout.dtype == x.dtype and dout.is_cuda and tuple(dout.shape) == (batch, dim, seqlen) and dout.stride(2) == 1,
+           "causal_conv1d_bwd: dout must match x in dtype and shape with stride(2) == 1")
+    with torch.cuda.device(x.device):
+        if dx_ is not None:
+            dx = dx_
+            _check(dx.dtype == x.dtype and dx.is_cuda and tuple(dx.shape) == (batch, dim, seqlen) and dx.stride(2) == 1,
+                   "causal_conv1d_bwd: dx must match x in dtype and shape with stride(2) == 1")
+        else:
+            dx = torch.empty(x.shape, device=x.device, dtype=x.dtype)
+        # fp32 accumulators for the atomics, cast back at the end (causal_conv1d.cpp:402-405,425)
+        dweight = torch.zeros((dim, width), device=x.device, dtype=torch.float32)
+        dbias = torch.zeros((dim,), device=x.device, dtype=torch.float32) if bias_ is not None else None
+        p = _lib.ConvBwdParams()
+        p.batch, p.dim, p.seqlen, p.width = batch, dim, seqlen, width
+        p.io_dtype, p.w_dtype, p.silu = _DT[x.dtype], _DT[weight.dtype], int(bool(silu_activation))
+        p.x_batch_stride, p.x_d_stride = x.stride(0), x.stride(1)
+        p.dout_batch_stride, p.dout_d_stride = dout.stride(0), dout.stride(1)
+        p.dx_batch_stride, p.dx_d_stride = dx.stride(0), dx.stride(1)
+        p.w_d_stride, p.w_width_stride = weight.stride(0), weight.stride(1)
+        p.x, p.weight, p.dout, p.dx = x.data_ptr(), weight.data_ptr(), dout.data_ptr(), dx.data_ptr()
+        p.bias = bias_.data_ptr() if bias_ is not None else None
+        p.dweight = dweight.data_ptr()
+        p.dbias = dbias.data_ptr() if dbias is not None else None
+        _lib.call("dimsum_causal_conv1d_bwd", p, _stream(x))
+    return [dx, dweight.to(weight.dtype), dbias.to(bias_.dtype) if bias_ is not None else None]
+
+
+def causal_conv1d_bwd_cond(x, weight, bias_, dout, dx_, silu_activation, init_x=None):
+    """causal_conv1d.cpp:429-510 -> [dx, dweight, dbias, dcond]; the conditioning input gets no gradient."""
+    return causal_conv1d_bwd(x, weight, bias_, dout, dx_, silu_activation) + [None]
+
+
+def causal_conv1d_update(x, conv_state, weight, bias_, silu_activation):
+    raise NotImplementedError("causal_conv1d_update (autoregressive decode) is outside the DiMSUM hot path")

@@ -1,0 +1,187 @@
+/*
+ * dimsum_b200 -- C ABI of the B200-native DiMSUM Mamba hot path (libdimsum_b200.so).
+ *
+ * Plain C: pointers, sizes, element strides, a CUDA stream handle.  No torch / ATen types.
+ * Every entry point validates its arguments, launches asynchronously on `stream`, never
+ * allocates device memory, never synchronises, and returns 0 or a negative dimsum_status;
+ * dimsum_last_error() gives the message of the calling thread's last failure.
+ *
+ * Which reference interface each entry replaces (paths relative to the reference tree):
+ *
+ *   dimsum_selective_scan_fwd   selective_scan_fwd()  mamba/csrc/selective_scan/selective_scan.cpp:226-336
+ *                               (pybind `selective_scan_cuda.fwd`, :495; params POD selective_scan.h:26-69)
+ *   dimsum_selective_scan_bwd   selective_scan_bwd()  selective_scan.cpp:338-492 (`.bwd`, :496; selective_scan.h:71-101)
+ *   dimsum_causal_conv1d_fwd    causal_conv1d_fwd() / causal_conv1d_fwd_cond()
+ *                               causal-conv1d/csrc/causal_conv1d.cpp:221-281, :283-347 (POD causal_conv1d.h:9-35)
+ *   dimsum_causal_conv1d_bwd    causal_conv1d_bwd() / causal_conv1d_bwd_cond()  causal_conv1d.cpp:349-427, :429-510
+ *   dimsum_token_gather         torch.gather on token orders, mamba/mamba_ssm/modules/mamba_simple.py:634,657 and the
+ *                               rearrange/flip/local_scan copies of dimsum/models_dim.py:1498-1524, :660-664,:700-701
+ *   dimsum_wavelet_packet_fwd   WaveDiMBlock._dwt_fast  dimsum/models_dim.py:572-586 (+ local_scan :662)
+ *   dimsum_wavelet_packet_inv   WaveDiMBlock._idwt_fast dimsum/models_dim.py:588-604 (+ local_reverse :701)
+ *
+ * All strides are in ELEMENTS of the tensor's own dtype.  The innermost (sequence) stride of every
+ * (batch, dim, seqlen) tensor is 1, as the reference requires (selective_scan.cpp:252-253).
+ */
+#ifndef DIMSUM_B200_H_
+#define DIMSUM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DIMSUM_ABI_VERSION 1
+
+typedef enum {
+    DIMSUM_OK = 0,
+    DIMSUM_ERR_INVALID = -1,       /* bad argument (shape, stride, alignment, null pointer)      */
+    DIMSUM_ERR_UNSUPPORTED = -2,   /* legal in the reference, not implemented here (no fallback) */
+    DIMSUM_ERR_CUDA = -3           /* CUDA runtime reported an error at launch                   */
+} dimsum_status;
+
+typedef enum { DIMSUM_F32 = 0, DIMSUM_F16 = 1, DIMSUM_BF16 = 2 } dimsum_dtype;
+
+/* ---- selective scan ------------------------------------------------------------------------
+ * u, delta, z, out, out_z : (batch, dim, seqlen) io_dtype, arbitrary batch / dim strides
+ * A                       : (dim, dstate) fp32
+ * B, C                    : (batch, n_groups, dstate, seqlen) io_dtype ("variable" B and C)
+ * D, delta_bias           : (dim) fp32 or NULL
+ * x                       : (batch, dim, n_chunks, 2*dstate) fp32 contiguous or NULL, chunk_len = 32,
+ *                           n_chunks = ceil(seqlen/32).  x[..., 2n+1] = state h_n after the chunk (so the
+ *                           reference's last_state = x[:, :, -1, 1::2] holds, selective_scan_interface.py:39),
+ *                           x[..., 2n] = h_n after the first 16 steps of the chunk: together the 16-step
+ *                           checkpoints the backward restarts from.  (The reference stores (prod a, h) per
+ *                           2048-step chunk, selective_scan_fwd_kernel.cuh:251-254; only its own backward
+ *                           kernel, replaced here, ever reads the even slots.)
+ * out                     : pre-gate y (needed by backward) or NULL (inference)
+ * z / out_z               : both NULL or both set; out_z = y * silu(z)
+ * perm                    : NULL, or int32[seqlen]: z is read at, and out_z written to, token perm[l]
+ *                           (scan-order gather folded into the kernel; inference only)
+ */
+typedef struct {
+    int64_t batch, dim, seqlen, dstate, n_groups, n_chunks, chunk_len;
+    int64_t io_dtype, delta_softplus;
+    int64_t u_batch_stride, u_d_stride;
+    int64_t delta_batch_stride, delta_d_stride;
+    int64_t z_batch_stride, z_d_stride;
+    int64_t out_batch_stride, out_d_stride;
+    int64_t out_z_batch_stride, out_z_d_stride;
+    int64_t A_d_stride, A_dstate_stride;
+    int64_t B_batch_stride, B_group_stride, B_dstate_stride;
+    int64_t C_batch_stride, C_group_stride, C_dstate_stride;
+    const void *u, *delta, *A, *B, *C, *D, *z, *delta_bias;
+    const int32_t *perm;
+    void *out, *out_z, *x;
+} dimsum_scan_fwd_params;
+
+int dimsum_selective_scan_fwd(const dimsum_scan_fwd_params *p, void *stream);
+
+/* Backward.  dB, dC are fp32 (batch, n_groups, dstate, seqlen) and dA (dim,dstate), dD, ddelta_bias (dim)
+ * fp32; ALL FIVE must be zero-initialised by the caller (they are accumulated with atomics, as in the
+ * reference: selective_scan.cpp:460-466).  du, ddelta, dz in io_dtype with their own strides (dz may be a
+ * view of a larger buffer, selective_scan_interface.py:933-934).  out_z_recompute: optional recomputed
+ * gated output (reference `recompute_out_z`).  x: the checkpoint tensor produced by the forward.
+ */
+typedef struct {
+    int64_t batch, dim, seqlen, dstate, n_groups, n_chunks, chunk_len;
+    int64_t io_dtype, delta_softplus;
+    int64_t u_batch_stride, u_d_stride;
+    int64_t delta_batch_stride, delta_d_stride;
+    int64_t z_batch_stride, z_d_stride;
+    int64_t out_batch_stride, out_d_stride;
+    int64_t dout_batch_stride, dout_d_stride;
+    int64_t du_batch_stride, du_d_stride;
+    int64_t ddelta_batch_stride, ddelta_d_stride;
+    int64_t dz_batch_stride, dz_d_stride;
+    int64_t out_z_batch_stride, out_z_d_stride;
+    int64_t A_d_stride, A_dstate_stride;
+    int64_t B_batch_stride, B_group_stride, B_dstate_stride;
+    int64_t C_batch_stride, C_group_stride, C_dstate_stride;
+    int64_t dB_batch_stride, dB_group_stride, dB_dstate_stride;
+    int64_t dC_batch_stride, dC_group_stride, dC_dstate_stride;
+    const void *u, *delta, *A, *B, *C, *D, *z, *delta_bias, *dout, *out, *x;
+    void *du, *ddelta, *dz, *out_z_recompute;
+    float *dA, *dB, *dC, *dD, *ddelta_bias;
+} dimsum_scan_bwd_params;
+
+int dimsum_selective_scan_bwd(const dimsum_scan_bwd_params *p, void *stream);
+
+/* ---- causal depthwise conv1d (+ optional SiLU) ----------------------------------------------
+ * x, out : (batch, dim, seqlen) io_dtype; weight (dim, width) and bias (dim) in w_dtype; width 2..4.
+ * perm   : NULL or int32[seqlen]; the conv runs over the permuted sequence x[:, :, perm[l]]
+ *          (token-order gather folded into the load, no permuted copy of x).
+ */
+typedef struct {
+    int64_t batch, dim, seqlen, width;
+    int64_t io_dtype, w_dtype, silu;
+    int64_t x_batch_stride, x_d_stride;
+    int64_t out_batch_stride, out_d_stride;
+    int64_t w_d_stride, w_width_stride;
+    const void *x, *weight, *bias;
+    const int32_t *perm;
+    void *out;
+} dimsum_conv_fwd_params;
+
+int dimsum_causal_conv1d_fwd(const dimsum_conv_fwd_params *p, void *stream);
+
+/* dweight (dim,width) and dbias (dim) are fp32 and must be zero-initialised (atomics, causal_conv1d.cpp:402-405). */
+typedef struct {
+    int64_t batch, dim, seqlen, width;
+    int64_t io_dtype, w_dtype, silu;
+    int64_t x_batch_stride, x_d_stride;
+    int64_t dout_batch_stride, dout_d_stride;
+    int64_t dx_batch_stride, dx_d_stride;
+    int64_t w_d_stride, w_width_stride;
+    const void *x, *weight, *bias, *dout;
+    void *dx;
+    float *dweight, *dbias;
+} dimsum_conv_bwd_params;
+
+int dimsum_causal_conv1d_bwd(const dimsum_conv_bwd_params *p, void *stream);
+
+/* ---- token-major gather: dst[b, l, :] = src[b, index[l], :]  for (batch, seqlen, channels) rows ---- */
+typedef struct {
+    int64_t batch, seqlen, channels, dtype;
+    int64_t src_batch_stride, src_token_stride;
+    int64_t dst_batch_stride, dst_token_stride;
+    const void *src;
+    const int32_t *index;
+    void *dst;
+} dimsum_gather_params;
+
+int dimsum_token_gather(const dimsum_gather_params *p, void *stream);
+
+/* ---- 2-level Haar wavelet packet with the reference's token/channel map -----------------------
+ * src, dst : (batch, grid*grid tokens, channels), token-major, channel stride 1; channels % 16 == 0, grid % 4 == 0.
+ * fwd : dst[b, pos[token'], c'] = coef ...   where pos = seq_of_token (NULL = identity) places the
+ *       transformed token at its position in the window scan (local_scan fused into the store).
+ * inv : reads src[b, pos[token'], c'] (local_reverse fused into the load) and reconstructs the image tokens.
+ * Both kernels compute the raw +-1 butterfly times `scale`: the forward transform uses scale = 1/16
+ * (two Haar levels of 1/2 each, then the reference's division by 4), the inverse uses scale = 1.
+ * Gradients reuse the same two kernels (wavelet_layer.py:22-33,50-65): d(fwd) = inv with scale 1/16,
+ * d(inv) = fwd with scale 1.
+ */
+typedef struct {
+    int64_t batch, grid, channels, dtype;
+    int64_t src_batch_stride, src_token_stride;
+    int64_t dst_batch_stride, dst_token_stride;
+    const void *src;
+    const int32_t *pos;
+    void *dst;
+    float scale;
+} dimsum_wavelet_params;
+
+int dimsum_wavelet_packet_fwd(const dimsum_wavelet_params *p, void *stream);
+int dimsum_wavelet_packet_inv(const dimsum_wavelet_params *p, void *stream);
+
+/* ---- misc --------------------------------------------------------------------------------- */
+int dimsum_abi_version(void);
+const char *dimsum_last_error(void);
+/* number of kernel launches issued by this library in this process (bench.py `gpu_launches`). */
+int64_t dimsum_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIMSUM_B200_H_ */
