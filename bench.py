@@ -1,0 +1,313 @@
+"""Contract benchmark: DiMSUM-L/2 forward latents/s (BASELINE.json metric) + selective-scan roofline.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3                     # this repo (hand-written sm_100a kernels)
+    python bench.py --impl reference --gpus 1 --steps 1 --warmup 0     # reference CPU path (oracle port) on the host cores
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[2]): DiMSUM-L/2 256px class-conditional CFG sampling, 256 synthetic latents
+(4x32x32 -> L=256 tokens) sharded contiguously over the N ranks; one STEP is one denoising evaluation of the 250-point
+Euler grid: v = model.forward_with_cfg(x, t, y, cfg_scale=4) on 2*256/N rows and x += dt*v.  value = 256 latents / step
+time (max over ranks) -- total work is fixed, so scaling is "strong".  Weights are random-init DiM-L/2 (459.9 M
+parameters) with the adaLN-zero layers re-randomised (otherwise the network output is identically zero).
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TOTAL_LATENTS = 256
+CFG_SCALE = 4.0
+NUM_GRID = 250
+D_INNER, D_STATE, SEQ = 1024, 16, 256
+
+
+def build_model(device, res=32, seed=0):
+    from dimsum_b200.models_dim import DiM_models
+    torch.manual_seed(seed)
+    with torch.device(device):
+        model = DiM_models["DiM-L/2"](img_resolution=res, in_channels=4, num_classes=1000, label_dropout=0.1)
+    g = torch.Generator(device="cpu").manual_seed(seed + 1)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if "adaLN_modulation" in n or n.startswith("final_layer.linear"):
+                p.copy_((torch.randn(p.shape, generator=g) * 0.02).to(p.device))
+    return model.eval()
+
+
+def make_inputs(n_total, res=32, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    z = torch.randn(n_total, 4, res, res, generator=g)
+    y = torch.randint(0, 1000, (n_total,), generator=g)
+    return z, y
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm = sorted(int(float(r[1])) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(float(self.rows[0][2])), "reasons": reasons, "samples": len(sm)}
+
+
+def measured_peak():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"], "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def scan_bytes(rows, s):
+    """Algorithmic bytes of one inference scan launch: reads u, delta, z, B, C, A, D, dt_bias; writes y."""
+    return s * (4 * rows * D_INNER * SEQ + 2 * rows * D_STATE * SEQ) + 4 * (D_INNER * D_STATE + 2 * D_INNER)
+
+
+def cpu_reference_step(sd, n_latents, seed=0):
+    """One CFG denoising evaluation of the oracle port on the host cores; returns seconds."""
+    from oracle import ref_model
+    z, y = make_inputs(n_latents, seed=seed)
+    x = torch.cat([z, z])
+    yy = torch.cat([y, torch.full_like(y, 1000)])
+    t = torch.full((2 * n_latents,), 0.5)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        v = ref_model.dim_forward_with_cfg_oracle(sd, x, t, yy, CFG_SCALE)
+    dt = time.perf_counter() - t0
+    assert torch.isfinite(v).all()
+    return dt
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU path (oracle port of DiM.forward_with_cfg on selective_scan_ref /
+    causal_conv1d_ref semantics) with all host threads, bounded sample of the same workload."""
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count())
+    model = build_model("cpu")
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    n = 1
+    for _ in range(args.warmup):
+        cpu_reference_step(sd, n)
+    times = [cpu_reference_step(sd, n) for _ in range(max(1, args.steps))]
+    sec = sum(times) / len(times)
+    val = n / sec
+    line = {
+        "impl": "reference", "metric": "DiMSUM-L/2 fwd latents/s", "value": val, "unit": "latents/s", "n_gpus": args.gpus,
+        "steps": len(times), "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "DiMSUM-L/2 256px CFG denoising evaluation (configs[2]), CPU reference path",
+                   "latents_per_step": n, "rows_per_step": 2 * n, "cfg_scale": CFG_SCALE, "tokens": SEQ},
+        "cpu_baseline": {"value": val, "unit": "latents/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{n} latent (2 CFG rows) x {len(times)} evaluation(s) of the 249-evaluation sampler"},
+        "e2e": {"value": val, "unit": "latents/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args, rank, local_rank, world):
+    import torch.distributed as dist
+    from dimsum_b200 import _lib
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cuda.matmul.allow_tf32 = True      # reference: dimsum/train.py:20-21
+    torch.backends.cudnn.allow_tf32 = True
+    model = build_model(dev)
+    autocast = torch.autocast("cuda", dtype=torch.bfloat16, enabled=args.dtype == "bf16")
+    n_total = args.latents
+    assert n_total % world == 0
+    n = n_total // world
+    z_all, y_all = make_inputs(n_total)
+    lo = rank * n
+    z, y = z_all[lo:lo + n], y_all[lo:lo + n]
+    x_host = torch.cat([z, z]).pin_memory()
+    y_host = torch.cat([y, torch.full_like(y, 1000)]).pin_memory()
+    t_host = torch.full((2 * n,), 0.5).pin_memory()
+    out_host = torch.empty_like(x_host).pin_memory()
+    x0 = x_host.to(dev)
+    yy = y_host.to(dev)
+    ts = torch.linspace(0, 1, NUM_GRID, device=dev)
+    ones = torch.ones(2 * n, device=dev)
+
+    scan_events = []
+    real_call = _lib.call
+
+    def timed_call(name, params, stream):
+        if name != "dimsum_selective_scan_fwd" or not timed_call.on:
+            return real_call(name, params, stream)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        real_call(name, params, stream)
+        e.record()
+        scan_events.append((s, e))
+
+    timed_call.on = False
+    _lib.call = timed_call
+
+    def step(x, i):
+        with torch.no_grad(), autocast:
+            v = model.forward_with_cfg(x, ones * ts[i], yy, cfg_scale=CFG_SCALE)
+        return x + (ts[i + 1] - ts[i]) * v.float()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ------------------------------------------------------------------ device-resident timing
+    x = x0.clone()
+    for i in range(args.warmup):
+        x = step(x, i)
+    barrier()
+    launches0 = _lib.launch_count()
+    with ClockSampler(local_rank) as clocks:
+        timed_call.on = True
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for i in range(args.steps):
+            x = step(x, args.warmup + i)
+        ev1.record()
+        barrier()
+        timed_call.on = False
+    launches = _lib.launch_count() - launches0
+    ms = ev0.elapsed_time(ev1) / args.steps
+    scan_ms = sum(s.elapsed_time(e) for s, e in scan_events) / max(1, len(scan_events))
+    assert torch.isfinite(x).all()
+
+    # ------------------------------------------------------------------ end to end: host buffers in, host buffers out
+    for i in range(min(2, args.warmup)):
+        xd = x_host.to(dev, non_blocking=True)
+        out_host.copy_(step(xd, i), non_blocking=True)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        xd = x_host.to(dev, non_blocking=True)
+        yd = y_host.to(dev, non_blocking=True)
+        td = t_host.to(dev, non_blocking=True)
+        with torch.no_grad(), autocast:
+            v = model.forward_with_cfg(xd, td, yd, cfg_scale=CFG_SCALE)
+        out_host.copy_(xd + (1.0 / (NUM_GRID - 1)) * v.float(), non_blocking=True)
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1) / args.steps
+
+    if world > 1:
+        tt = torch.tensor([ms, ms_e2e, scan_ms], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms, ms_e2e, scan_ms = tt.tolist()
+        lc = torch.tensor([launches], device=dev)
+        dist.all_reduce(lc)
+        launches = int(lc.item())
+
+    if rank == 0:
+        s = 4 if args.dtype == "fp32" else 2
+        peak, how = measured_peak()
+        by = scan_bytes(2 * n, s)
+        achieved = by / (scan_ms * 1e-3) / 1e9
+        traffic = None
+        tr_path = os.path.join(ROOT, "profiles", "scan_fwd_traffic.json")
+        if os.path.exists(tr_path):
+            try:
+                tr = json.load(open(tr_path))
+                traffic = tr.get(args.dtype, {}).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": "DiMSUM-L/2 fwd latents/s", "value": n_total / (ms * 1e-3), "unit": "latents/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32" if args.dtype == "fp32" else "bf16", "data": "synthetic",
+            "config": {"workload": "DiMSUM-L/2 256px CFG denoising evaluation (BASELINE configs[2]): 256 latents sharded "
+                                   "over the ranks, 2x rows with CFG, one Euler step of the 250-point grid per step",
+                       "latents_total": n_total, "rows_per_rank": 2 * n, "tokens": SEQ, "d_inner": D_INNER, "d_state": D_STATE,
+                       "cfg_scale": CFG_SCALE, "matmul": "tf32" if args.dtype == "fp32" else "bf16 autocast",
+                       "l2": "working set per step >> 126 MB L2 (xz alone is %.0f MB per mixer call)" % (2 * n * 2048 * 256 * s / 1e6),
+                       "params": sum(p.numel() for p in model.parameters())},
+            "e2e": {"value": n_total / (ms_e2e * 1e-3), "unit": "latents/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": (x_host.numel() * 4 + y_host.numel() * 8 + t_host.numel() * 4) * world,
+                    "d2h_bytes_per_step": out_host.numel() * 4 * world},
+            "gpu_launches": launches,
+            "roofline": {"kernel": "scan_fwd_kernel (selective scan forward, inference)", "bound": "hbm",
+                         "achieved": achieved, "peak": peak, "peak_source": how + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes_per_launch": by,
+                         "avg_launch_ms": scan_ms, "launches_timed": len(scan_events),
+                         "share_of_step": scan_ms * 32 / ms},
+            "clocks": clocks.summary(),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            torch.set_num_threads(os.cpu_count())
+            sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+            sec = cpu_reference_step(sd, 1)
+            line["cpu_baseline"] = {"value": 1 / sec, "unit": "latents/s", "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": "1 latent (2 CFG rows), 1 of the 249 evaluations, oracle port of the reference "
+                                              "CPU path (selective_scan_ref / causal_conv1d_ref semantics), %.1f s" % sec}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--latents", type=int, default=TOTAL_LATENTS)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    args.warmup = max(args.warmup, 3)
+    run_b200(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

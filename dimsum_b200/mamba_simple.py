@@ -1,0 +1,129 @@
+"""`Mamba` / `CondMamba` mixers on the B200 kernels (reference: mamba/mamba_ssm/modules/mamba_simple.py:42-380, :438-701).
+
+Same constructor arguments, parameter names and state-dict keys as the reference, so released checkpoints load
+unchanged (`in_proj`, `conv1d`, `x_proj`, `dt_proj`, `cond_proj`, `A_log`, `D`, `out_proj`, and the
+`zigzag_paths[_reverse]` buffers when scan_type != "none").
+
+What is different is how the token order is applied.  The reference gathers `xz` (batch, 2*d_inner, L) and the output
+(batch, L, d_model) into permuted copies (mamba_simple.py:634,657).  Here the conv reads x through the table, the scan
+reads z and writes its gated output through the table, so out_proj already sees natural token order and no permuted
+copy is ever materialised.  `forward(..., order=perm)` lets the enclosing block pass the implicit
+transpose / flip orders of the released configuration through the same mechanism.
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import causal_conv1d_cuda, selective_scan_cuda
+from .selective_scan_interface import mamba_inner_fn
+
+
+class Mamba(nn.Module):
+    def __init__(self, d_model, d_state=16, d_conv=4, expand=2, dt_rank="auto", dt_min=0.001, dt_max=0.1,
+                 dt_init="random", dt_scale=1.0, dt_init_floor=1e-4, conv_bias=True, bias=False, use_fast_path=True,
+                 layer_idx=None, device=None, dtype=None, scan_type="none", d_cond=None, **kwargs):
+        fk = {"device": device, "dtype": dtype}
+        super().__init__()
+        if scan_type == "v2":
+            raise NotImplementedError("bidirectional scan_type='v2' is not part of the DiMSUM hot path")
+        self.d_model, self.d_state, self.d_conv, self.expand = d_model, d_state, d_conv, expand
+        self.d_inner = int(expand * d_model)
+        self.dt_rank = math.ceil(d_model / 16) if dt_rank == "auto" else dt_rank
+        self.use_fast_path, self.layer_idx, self.scan_type, self.d_cond = use_fast_path, layer_idx, scan_type, d_cond
+        self.in_proj = nn.Linear(d_model, self.d_inner * 2, bias=bias, **fk)
+        self.conv1d = nn.Conv1d(self.d_inner, self.d_inner, kernel_size=d_conv, groups=self.d_inner, padding=d_conv - 1,
+                                bias=conv_bias, **fk)
+        self.activation = "silu"
+        self.x_proj = nn.Linear(self.d_inner, self.dt_rank + 2 * d_state, bias=False, **fk)
+        self.dt_proj = nn.Linear(self.dt_rank, self.d_inner, bias=True, **fk)
+        if d_cond is not None:
+            # kept for checkpoint compatibility; its output never influences the result
+            self.cond_proj = nn.Linear(d_cond, self.d_inner, bias=True, **fk)
+        # dt_proj keeps the variance of delta at init; its bias is softplus^-1 of a log-uniform step in [dt_min, dt_max]
+        std = self.dt_rank ** -0.5 * dt_scale
+        if dt_init == "constant":
+            nn.init.constant_(self.dt_proj.weight, std)
+        elif dt_init == "random":
+            nn.init.uniform_(self.dt_proj.weight, -std, std)
+        else:
+            raise NotImplementedError
+        dt = torch.exp(torch.rand(self.d_inner, **fk) * (math.log(dt_max) - math.log(dt_min)) + math.log(dt_min))
+        dt = dt.clamp(min=dt_init_floor)
+        with torch.no_grad():
+            self.dt_proj.bias.copy_(dt + torch.log(-torch.expm1(-dt)))
+        self.dt_proj.bias._no_reinit = True
+        # S4D-real: A[d, n] = -(n + 1), stored as log
+        A = torch.arange(1, d_state + 1, dtype=torch.float32, device=device).repeat(self.d_inner, 1)
+        self.A_log = nn.Parameter(torch.log(A))
+        self.A_log._no_weight_decay = True
+        self.D = nn.Parameter(torch.ones(self.d_inner, device=device))
+        self.D._no_weight_decay = True
+        self.out_proj = nn.Linear(self.d_inner, d_model, bias=bias, **fk)
+        self.register_buffer("zigzag_paths", kwargs.get("zigzag_paths", None))
+        self.register_buffer("zigzag_paths_reverse", kwargs.get("zigzag_paths_reverse", None))
+        self._order_cache = {}
+
+    def _table_order(self, device):
+        if not self.scan_type.startswith(("zigma", "sweep", "jpeg")):
+            return None
+        key = (self.layer_idx, device)
+        if key not in self._order_cache:
+            self._order_cache[key] = self.zigzag_paths[self.layer_idx].to(device=device, dtype=torch.int32).contiguous()
+        return self._order_cache[key]
+
+    def forward(self, hidden_states, cond_emb=None, inference_params=None, order=None):
+        """hidden_states (B, L, D) -> (B, L, D).  `order`: optional int32 (L,) CUDA table; the conv + scan then run over
+        tokens order[0], order[1], ... while input and output stay in natural token order."""
+        if inference_params is not None:
+            raise NotImplementedError("autoregressive decode (inference_params) is outside the DiMSUM hot path")
+        table = self._table_order(hidden_states.device)
+        if table is not None and order is not None:
+            order = order[table.long()].contiguous()
+        elif table is not None:
+            order = table
+        if order is not None and torch.is_grad_enabled():
+            # training through an explicit order: gather token rows (coalesced), run the plain composite, gather back
+            from .scanning_orders import permute_tokens, reverse_permut_np
+            inv = torch.from_numpy(reverse_permut_np(order.cpu().numpy())).to(device=order.device, dtype=torch.int32)
+            return permute_tokens(self._mix(permute_tokens(hidden_states.contiguous(), order, inv), None), inv, order)
+        return self._mix(hidden_states, order)
+
+    def _mix(self, hidden_states, order):
+        batch, seqlen, _ = hidden_states.shape
+        # in_proj with the transpose folded in: (2*d_inner, B*L) viewed as (B, 2*d_inner, L), L contiguous
+        xz = (self.in_proj.weight @ hidden_states.reshape(batch * seqlen, -1).t()).view(-1, batch, seqlen).transpose(0, 1)
+        if self.in_proj.bias is not None:
+            xz = xz + self.in_proj.bias.to(xz.dtype).view(1, -1, 1)
+        A = -torch.exp(self.A_log.float())
+        if order is None:
+            return mamba_inner_fn(xz, self.conv1d.weight, self.conv1d.bias, self.x_proj.weight, self.dt_proj.weight,
+                                  self.out_proj.weight, self.out_proj.bias, A, None, None, self.D.float(),
+                                  delta_bias=self.dt_proj.bias.float(), delta_softplus=True)
+        return self._ordered_inference(xz, A, order)
+
+    def _ordered_inference(self, xz, A, order):
+        """conv -> x_proj -> dt_proj -> scan -> out_proj with the token order folded into the kernels."""
+        B_, twoD, L = xz.shape
+        Dm = twoD // 2
+        N, rank = self.d_state, self.dt_rank
+        x, z = xz[:, :Dm], xz[:, Dm:]
+        x_proj_w, dt_w, out_w = self.x_proj.weight, self.dt_proj.weight, self.out_proj.weight
+        if torch.is_autocast_enabled():
+            dt_ = torch.get_autocast_dtype("cuda")
+            x_proj_w, dt_w, out_w = x_proj_w.to(dt_), dt_w.to(dt_), out_w.to(dt_)
+        conv_w = self.conv1d.weight.reshape(Dm, -1)
+        u = causal_conv1d_cuda.causal_conv1d_fwd(x, conv_w, self.conv1d.bias, True, perm=order)   # permuted order
+        x_dbl = F.linear(u.transpose(1, 2).reshape(B_ * L, Dm), x_proj_w)
+        delta = (dt_w @ x_dbl[:, :rank].t()).view(Dm, B_, L).transpose(0, 1)
+        Bm = x_dbl[:, rank:rank + N].view(B_, L, 1, N).permute(0, 2, 3, 1).contiguous()
+        Cm = x_dbl[:, rank + N:].view(B_, L, 1, N).permute(0, 2, 3, 1).contiguous()
+        _, _, out_z = selective_scan_cuda.fwd(u, delta, A, Bm, Cm, self.D.float(), z, self.dt_proj.bias.float(), True,
+                                              need_out=False, need_x=False, perm=order)           # natural order again
+        return F.linear(out_z.transpose(1, 2), out_w, self.out_proj.bias)
+
+
+class CondMamba(Mamba):
+    """`CondMamba` (mamba_simple.py:438): identical maths to `Mamba` -- the conditioning embedding only ever served as
+    the conv's output buffer in the reference (causal_conv1d.cpp:326) -- plus the `cond_proj` parameters."""

@@ -297,6 +297,43 @@ def gen_mamba_inner(ref):
     print("mamba_inner: ok")
 
 
+def gen_model(ref):
+    """Reference `DiM` (models_dim.py:1557) in the released wiring (block_type=combined, cond_mamba, rms_norm,
+    fused_add_norm, learnable_pe, shared attention every 4 layers, scan_type=none) at toy width, run on CPU through
+    the reference's slow path (`*_ref` ops).  adaLN / final layers are re-randomised -- otherwise the
+    adaLN-zero init makes the output identically zero and parity vacuous."""
+    from oracle.ref_loader import load_reference_model_module
+    md = load_reference_model_module()
+    for name, res, hidden, depth in (("toy256", 32, 64, 5), ("toy512", 64, 32, 4)):
+        torch.manual_seed(11)
+        m = md.DiM(img_resolution=res, in_channels=4, hidden_size=hidden, depth=depth, num_classes=10, label_dropout=0.1,
+                   scan_type="none", block_type="combined", cond_mamba=True, rms_norm=True, fused_add_norm=True,
+                   learnable_pe=True, use_attn_every_k_layers=4, ssm_cfg=dict(use_fast_path=False))
+        m.eval()
+        g = torch.Generator().manual_seed(12)
+        with torch.no_grad():
+            for n, prm in m.named_parameters():
+                if "adaLN_modulation" in n or n.startswith("final_layer.linear"):
+                    prm.copy_(torch.randn(prm.shape, generator=g) * (0.2 if "adaLN" in n else 0.05))
+                if n.endswith("norm.weight") or n.endswith("norm_2.weight"):
+                    prm.copy_(1.0 + 0.1 * torch.randn(prm.shape, generator=g))
+        x = torch.randn(2, 4, res, res, generator=g)
+        t = torch.rand(2, generator=g)
+        y = torch.randint(0, 10, (2,), generator=g)
+        with torch.no_grad():
+            out = m(x, t, y)
+            xc = torch.cat([x, x], 0)
+            yc = torch.cat([y, torch.full_like(y, 10)], 0)
+            out_cfg = m.forward_with_cfg(xc, torch.cat([t, t]), yc, cfg_scale=4.0)
+        store = {"in/x": x.numpy(), "in/t": t.numpy(), "in/y": y.numpy(), "out/plain": out.numpy(),
+                 "out/cfg4": out_cfg.numpy(), "cfg/res": np.asarray(res), "cfg/hidden": np.asarray(hidden),
+                 "cfg/depth": np.asarray(depth)}
+        for k, v in m.state_dict().items():
+            store["sd/" + k] = v.numpy()
+        np.savez_compressed(os.path.join(OUT, f"model_{name}.npz"), **store)
+        print("model", name, "ok; |out| max", out.abs().max().item(), "params", sum(p.numel() for p in m.parameters()))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
@@ -306,6 +343,7 @@ def main():
     gen_conv(ref)
     gen_wavelet(ref)
     gen_mamba_inner(ref)
+    gen_model(ref)
     total = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
     print("golden bytes:", total)
 

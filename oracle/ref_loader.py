@@ -66,3 +66,84 @@ def load_reference():
         wavelet_layer=wavelet_layer,
     )
     return ns
+
+
+def load_reference_model_module():
+    """Import the reference `models_dim` on CPU: timm 0.9.12 is absent, so the three timm classes it uses are
+    restated as minimal stubs (same parameter names / maths), the Triton RMSNorm kernel is routed to the
+    reference's own `rms_norm_ref`, and the Mamba slow path (use_fast_path=False) is pointed at the `*_ref` ops.
+    """
+    import torch
+    import torch.nn as nn
+    import torch.nn.functional as F
+
+    load_reference()
+    if "models_dim" in sys.modules:
+        return sys.modules["models_dim"]
+
+    class PatchEmbed(nn.Module):  # timm.layers.PatchEmbed: Conv2d(k=stride=patch) -> (B, N, C)
+        def __init__(self, img_size=224, patch_size=16, in_chans=3, embed_dim=768, bias=True):
+            super().__init__()
+            self.patch_size = (patch_size, patch_size)
+            self.num_patches = (img_size // patch_size) ** 2
+            self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=patch_size, stride=patch_size, bias=bias)
+
+        def forward(self, x):
+            return self.proj(x).flatten(2).transpose(1, 2)
+
+    class Attention(nn.Module):  # timm.models.vision_transformer.Attention (fused path)
+        def __init__(self, dim, num_heads=8, qkv_bias=False, **kw):
+            super().__init__()
+            self.num_heads, self.head_dim = num_heads, dim // num_heads
+            self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+            self.proj = nn.Linear(dim, dim)
+
+        def forward(self, x):
+            B, N, C = x.shape
+            q, k, v = self.qkv(x).reshape(B, N, 3, self.num_heads, self.head_dim).permute(2, 0, 3, 1, 4).unbind(0)
+            x = F.scaled_dot_product_attention(q, k, v)
+            return self.proj(x.transpose(1, 2).reshape(B, N, C))
+
+    class Mlp(nn.Module):
+        def __init__(self, in_features, hidden_features=None, act_layer=nn.GELU, drop=0.0):
+            super().__init__()
+            self.fc1 = nn.Linear(in_features, hidden_features)
+            self.act = act_layer()
+            self.fc2 = nn.Linear(hidden_features, in_features)
+
+        def forward(self, x):
+            return self.fc2(self.act(self.fc1(x)))
+
+    timm = types.ModuleType("timm")
+    timm.__path__ = []
+    for name in ("timm.models", "timm.models.vision_transformer", "timm.layers", "timm.models.layers"):
+        mod = types.ModuleType(name)
+        mod.__path__ = []
+        sys.modules[name] = mod
+    sys.modules["timm"] = timm
+    vt = sys.modules["timm.models.vision_transformer"]
+    vt.Attention, vt.Mlp, vt.PatchEmbed = Attention, Mlp, PatchEmbed
+    sys.modules["timm.layers"].use_fused_attn = lambda: True
+    for m in ("timm.layers", "timm.models.layers"):
+        sys.modules[m].DropPath = nn.Identity
+        sys.modules[m].trunc_normal_ = nn.init.trunc_normal_
+        sys.modules[m].lecun_normal_ = nn.init.normal_
+        sys.modules[m].to_2tuple = lambda v: (v, v)
+    sys.path.insert(0, os.path.join(REFERENCE_ROOT, "dimsum", "pe"))
+
+    import mamba_ssm.ops.triton.layernorm as ln
+    from mamba_ssm.ops.selective_scan_interface import selective_scan_ref
+    from causal_conv1d.causal_conv1d_interface import causal_conv1d_ref
+
+    def rms_norm_fn(x, weight, bias, residual=None, prenorm=False, residual_in_fp32=False, eps=1e-6):
+        return ln.rms_norm_ref(x, weight, bias, residual=residual, eps=eps, prenorm=prenorm, upcast=True)
+
+    ln.rms_norm_fn = rms_norm_fn
+    ln.RMSNorm.forward = lambda self, x, residual=None, prenorm=False, residual_in_fp32=False: rms_norm_fn(
+        x, self.weight, self.bias, residual=residual, eps=self.eps, prenorm=prenorm)
+    import mamba_ssm.modules.mamba_simple as ms
+    ms.selective_scan_fn = selective_scan_ref
+    ms.causal_conv1d_fn = causal_conv1d_ref
+    import models_dim
+    models_dim.rms_norm_fn = rms_norm_fn
+    return models_dim

@@ -93,3 +93,17 @@ def test_mamba_inner_oracle_matches_reference():
     out = ref_ops.mamba_inner_oracle(c["xz"], c["conv_w"], c["conv_b"], c["x_proj_w"], c["dt_proj_w"], c["out_proj_w"],
                                      None, c["A"], c["D"], c["delta_bias"], perm=c["perm"], perm_rev=c["perm_rev"])
     assert rel_err(out, c["out"]) <= 2e-6
+
+
+@pytest.mark.parametrize("name", ["toy256", "toy512"])
+def test_model_oracle_matches_reference(name):
+    from oracle import ref_model
+    raw = np.load(os.path.join(GOLDEN, f"model_{name}.npz"))
+    sd = {k[3:]: torch.from_numpy(raw[k].copy()) for k in raw.files if k.startswith("sd/")}
+    x, t, y = (torch.from_numpy(raw[f"in/{k}"]) for k in ("x", "t", "y"))
+    with torch.no_grad():
+        out = ref_model.dim_forward_oracle(sd, x, t, y)
+        cfg = ref_model.dim_forward_with_cfg_oracle(sd, torch.cat([x, x]), torch.cat([t, t]),
+                                                    torch.cat([y, torch.full_like(y, 10)]), 4.0)
+    assert rel_err(out, torch.from_numpy(raw["out/plain"])) <= 2e-6
+    assert rel_err(cfg, torch.from_numpy(raw["out/cfg4"])) <= 2e-6
