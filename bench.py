@@ -40,7 +40,7 @@ def build_model(device, res=32, seed=0):
         for n, p in model.named_parameters():
             if "adaLN_modulation" in n or n.startswith("final_layer.linear"):
                 p.copy_((torch.randn(p.shape, generator=g) * 0.02).to(p.device))
-    return model.eval()
+    return model.to(device).eval()    # buffers built from numpy tables are created on the CPU
 
 
 def make_inputs(n_total, res=32, seed=0):

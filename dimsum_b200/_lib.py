@@ -110,6 +110,8 @@ ConvFwdParams = STRUCTS["dimsum_conv_fwd_params"]
 ConvBwdParams = STRUCTS["dimsum_conv_bwd_params"]
 GatherParams = STRUCTS["dimsum_gather_params"]
 WaveletParams = STRUCTS["dimsum_wavelet_params"]
+RowwiseParams = STRUCTS["dimsum_rowwise_params"]
+RmsnormParams = STRUCTS["dimsum_rmsnorm_params"]
 
 ENTRY_POINTS = {
     "dimsum_selective_scan_fwd": ScanFwdParams,
@@ -119,6 +121,9 @@ ENTRY_POINTS = {
     "dimsum_token_gather": GatherParams,
     "dimsum_wavelet_packet_fwd": WaveletParams,
     "dimsum_wavelet_packet_inv": WaveletParams,
+    "dimsum_modulate": RowwiseParams,
+    "dimsum_gate_residual": RowwiseParams,
+    "dimsum_add_rmsnorm": RmsnormParams,
 }
 
 

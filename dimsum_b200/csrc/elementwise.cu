@@ -1,0 +1,148 @@
+// Token-major glue around the mixer for sm_100a: adaLN modulate and gated residual with the scan order folded into the
+// row index (so the transpose / flip / table orders of DiMSUM cost no extra pass and no permuted copy), and the fused
+// residual-add + RMSNorm that the reference runs as a Triton kernel (mamba_ssm/ops/triton/layernorm.py:62-118).
+// All three are pure streaming kernels: 16-byte coalesced row accesses, one pass.
+#include "common.cuh"
+
+namespace dimsum {
+namespace {
+
+template <typename T, bool kGate>
+__global__ void __launch_bounds__(256) rowwise_kernel(const dimsum_rowwise_params p) {
+    constexpr int VEC = Io<T>::kVec;
+    const int vpt = (int)(p.channels / VEC);
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t total = p.batch * p.seqlen * vpt;
+    if (gid >= total) return;
+    const int v = (int)(gid % vpt);
+    const int64_t t = gid / vpt;
+    const int l = (int)(t % p.seqlen);
+    const int64_t b = t / p.seqlen;
+    const int src_l = p.idx != nullptr ? p.idx[l] : l;
+    const int c0 = v * VEC;
+    float a[VEC], o[VEC];
+    if (!kGate) {
+        float sh[VEC], sc[VEC];
+        Io<T>::ldv(reinterpret_cast<const T *>(p.x) + b * p.x_batch_stride + (int64_t)src_l * p.x_token_stride + c0, a);
+        Io<T>::ldv(reinterpret_cast<const T *>(p.shift) + b * p.vec_row_stride + c0, sh);
+        Io<T>::ldv(reinterpret_cast<const T *>(p.scale) + b * p.vec_row_stride + c0, sc);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) o[i] = fmaf(a[i], 1.f + sc[i], sh[i]);
+    } else {
+        float m[VEC], g[VEC];
+        Io<T>::ldv(reinterpret_cast<const T *>(p.x) + b * p.x_batch_stride + (int64_t)l * p.x_token_stride + c0, a);
+        Io<T>::ldv(reinterpret_cast<const T *>(p.m) + b * p.m_batch_stride + (int64_t)src_l * p.m_token_stride + c0, m);
+        Io<T>::ldv(reinterpret_cast<const T *>(p.gate) + b * p.vec_row_stride + c0, g);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) o[i] = fmaf(g[i], m[i], a[i]);
+    }
+    Io<T>::stv(reinterpret_cast<T *>(p.dst) + b * p.dst_batch_stride + (int64_t)l * p.dst_token_stride + c0, o);
+}
+
+// one warp per row; the row lives in registers between the two passes (channels <= 32 * 16 * VEC per warp loop)
+template <typename T>
+__global__ void __launch_bounds__(256) add_rmsnorm_kernel(const dimsum_rmsnorm_params p) {
+    constexpr int VEC = Io<T>::kVec;
+    constexpr int kMaxIter = 8;                       // up to 32 lanes * 8 * VEC channels (1024 fp32, 2048 16-bit)
+    const int warp = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (warp >= p.rows) return;
+    const int nvec = (int)(p.channels / VEC);
+    const T *x = reinterpret_cast<const T *>(p.x) + (int64_t)warp * p.x_row_stride;
+    const float *res = p.residual != nullptr ? reinterpret_cast<const float *>(p.residual) + (int64_t)warp * p.channels : nullptr;
+    float *res_out = p.res_out != nullptr ? reinterpret_cast<float *>(p.res_out) + (int64_t)warp * p.channels : nullptr;
+    float vals[kMaxIter][VEC];
+    float ss = 0.f;
+#pragma unroll
+    for (int it = 0; it < kMaxIter; ++it) {
+        const int v = lane + it * 32;
+        if (v < nvec) {
+            Io<T>::ldv(x + v * VEC, vals[it]);
+            if (res != nullptr) {
+#pragma unroll
+                for (int i = 0; i < VEC; i += 4) {
+                    const float4 r = *reinterpret_cast<const float4 *>(res + v * VEC + i);
+                    vals[it][i] += r.x; vals[it][i + 1] += r.y; vals[it][i + 2] += r.z; vals[it][i + 3] += r.w;
+                }
+            }
+            if (res_out != nullptr) {
+#pragma unroll
+                for (int i = 0; i < VEC; i += 4)
+                    *reinterpret_cast<float4 *>(res_out + v * VEC + i) =
+                        make_float4(vals[it][i], vals[it][i + 1], vals[it][i + 2], vals[it][i + 3]);
+            }
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) ss = fmaf(vals[it][i], vals[it][i], ss);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float rstd = rsqrtf(ss / (float)p.channels + p.eps);
+    const float *w = reinterpret_cast<const float *>(p.weight);
+    T *y = reinterpret_cast<T *>(p.y) + (int64_t)warp * p.y_row_stride;
+#pragma unroll
+    for (int it = 0; it < kMaxIter; ++it) {
+        const int v = lane + it * 32;
+        if (v < nvec) {
+            float o[VEC];
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) o[i] = vals[it][i] * rstd * w[v * VEC + i];
+            Io<T>::stv(y + v * VEC, o);
+        }
+    }
+}
+
+int rowwise_entry(const dimsum_rowwise_params *p, bool gate, void *stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    const char *who = gate ? "gate_residual" : "modulate";
+    DIMSUM_REQUIRE(p != nullptr && p->x && p->dst, DIMSUM_ERR_INVALID, "%s: null pointer", who);
+    DIMSUM_REQUIRE(gate ? (p->m && p->gate) : (p->shift && p->scale), DIMSUM_ERR_INVALID, "%s: null operand", who);
+    DIMSUM_REQUIRE(p->batch >= 0 && p->seqlen > 0 && p->channels > 0, DIMSUM_ERR_INVALID, "%s: bad sizes", who);
+    DIMSUM_REQUIRE(p->dtype >= 0 && p->dtype <= 2, DIMSUM_ERR_INVALID, "%s: unknown dtype", who);
+    const int vec = p->dtype == DIMSUM_F32 ? 4 : 8;
+    bool ok = p->channels % vec == 0 && aligned16(p->x) && aligned16(p->dst) && p->x_batch_stride % vec == 0 &&
+              p->x_token_stride % vec == 0 && p->dst_batch_stride % vec == 0 && p->dst_token_stride % vec == 0 &&
+              p->vec_row_stride % vec == 0;
+    if (gate) ok = ok && aligned16(p->m) && aligned16(p->gate) && p->m_batch_stride % vec == 0 && p->m_token_stride % vec == 0;
+    else ok = ok && aligned16(p->shift) && aligned16(p->scale);
+    DIMSUM_REQUIRE(ok, DIMSUM_ERR_UNSUPPORTED, "%s: rows must be 16-byte aligned multiples of 16 bytes", who);
+    DIMSUM_REQUIRE(p->dst != p->x || p->idx == nullptr || gate, DIMSUM_ERR_INVALID, "%s: in-place gather is not supported", who);
+    if (p->batch == 0) return DIMSUM_OK;
+    const int64_t total = p->batch * p->seqlen * (p->channels / vec);
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+#define LAUNCH(T)                                                                   \
+    if (gate) rowwise_kernel<T, true><<<blocks, 256, 0, stream>>>(*p);              \
+    else rowwise_kernel<T, false><<<blocks, 256, 0, stream>>>(*p);
+    if (p->dtype == DIMSUM_F32) { LAUNCH(float) }
+    else if (p->dtype == DIMSUM_BF16) { LAUNCH(__nv_bfloat16) }
+    else { LAUNCH(__half) }
+#undef LAUNCH
+    return check_launch(who);
+}
+
+}  // namespace
+}  // namespace dimsum
+
+using namespace dimsum;
+
+extern "C" int dimsum_modulate(const dimsum_rowwise_params *p, void *stream) { return rowwise_entry(p, false, stream); }
+extern "C" int dimsum_gate_residual(const dimsum_rowwise_params *p, void *stream) { return rowwise_entry(p, true, stream); }
+
+extern "C" int dimsum_add_rmsnorm(const dimsum_rmsnorm_params *p, void *stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    DIMSUM_REQUIRE(p != nullptr && p->x && p->weight && p->y, DIMSUM_ERR_INVALID, "add_rmsnorm: null pointer");
+    DIMSUM_REQUIRE(p->rows >= 0 && p->channels > 0, DIMSUM_ERR_INVALID, "add_rmsnorm: bad sizes");
+    DIMSUM_REQUIRE(p->dtype >= 0 && p->dtype <= 2, DIMSUM_ERR_INVALID, "add_rmsnorm: unknown dtype");
+    const int vec = p->dtype == DIMSUM_F32 ? 4 : 8;
+    DIMSUM_REQUIRE(p->channels % vec == 0 && p->channels <= 32 * 8 * vec, DIMSUM_ERR_UNSUPPORTED,
+                   "add_rmsnorm: channels %lld not supported (multiple of %d, at most %d)", (long long)p->channels, vec, 32 * 8 * vec);
+    DIMSUM_REQUIRE(aligned16(p->x) && aligned16(p->y) && p->x_row_stride % vec == 0 && p->y_row_stride % vec == 0 &&
+                       (p->residual == nullptr || aligned16(p->residual)) && (p->res_out == nullptr || aligned16(p->res_out)),
+                   DIMSUM_ERR_UNSUPPORTED, "add_rmsnorm: rows must be 16-byte aligned");
+    if (p->rows == 0) return DIMSUM_OK;
+    const unsigned blocks = (unsigned)((p->rows * 32 + 255) / 256);
+    if (p->dtype == DIMSUM_F32) add_rmsnorm_kernel<float><<<blocks, 256, 0, stream>>>(*p);
+    else if (p->dtype == DIMSUM_BF16) add_rmsnorm_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(*p);
+    else add_rmsnorm_kernel<__half><<<blocks, 256, 0, stream>>>(*p);
+    return check_launch("add_rmsnorm");
+}

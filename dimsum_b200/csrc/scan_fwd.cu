@@ -2,25 +2,29 @@
 //
 // Replaces selective_scan_fwd_kernel (mamba/csrc/selective_scan/selective_scan_fwd_kernel.cuh:67-303).
 // Design (B200-first, not a port):
-//   * one CTA = one batch row x a slab of 128 channels; one THREAD owns one channel row and walks the
-//     sequence with all <=16 states in registers as 8 packed f32x2 pairs (FFMA2/FMUL2) -- no cross-lane
-//     scan, so 4 FP ops + 1 exp per state-step instead of the 6 of a lane-split scan;
-//   * the sequence is processed in LC-step chunks.  Per chunk the CTA (a) loads u/delta with coalesced
-//     128-bit loads, applies bias+softplus, and parks fp32 delta/u in padded shared memory, together with
-//     the B/C tile transposed to [l][n] (read later as warp-wide broadcasts, so B/C are fetched once per
-//     128 channels instead of once per channel as in the reference), (b) runs the per-thread recurrence
-//     reading its row with conflict-free LDS.128, (c) writes y through the same padded tile and gates it
-//     with silu(z) on the coalesced way out;
-//   * part of the 16 exps per step can run as a polynomial on the FMA pipe (kPoly pairs), because at
-//     16 MUFU lanes/clk/SM the exp unit, not HBM, is the first limiter of this kernel.
+//   * one CTA = one batch row x a slab of 128 channels; one THREAD owns one channel row and walks the sequence with all
+//     <=16 states in registers as 8 packed f32x2 pairs (FFMA2 / FMUL2) -- no cross-lane scan, so 4 FP ops + 1 exp per
+//     state-step instead of the 6 of a lane-split scan;
+//   * the sequence is cut into chunks of 64 bytes per row (16 fp32 / 32 bf16 steps).  The raw u / delta / z tiles of
+//     chunk c+1 stream into shared memory with cp.async (16-byte, fully coalesced, no registers) WHILE chunk c is being
+//     scanned: a 2-stage software pipeline, so HBM latency is hidden behind the exp-bound recurrence even at 12 warps/SM;
+//   * tiles keep the storage dtype and an 80-byte row pitch, which makes the per-thread 128-bit row reads bank-conflict
+//     free; bias + softplus, the D skip and the silu(z) gate are applied by the scanning thread itself, which overwrites
+//     its u slot with the gated output, so the epilogue is a pure coalesced 128-bit copy-out;
+//   * the B / C tile is fetched one chunk ahead through registers and parked transposed as [l][n] fp32 (pitch 20), read
+//     as warp-wide 128-bit broadcasts: B and C are fetched once per 128 channels, not once per channel as in the reference;
+//   * kPoly of the 8 state pairs evaluate 2^x as a Cody-Waite polynomial on the FMA pipe instead of MUFU.EX2, because at
+//     16 SFU lanes/clk/SM the exp unit -- not HBM -- is the first limiter of this kernel.
 #include "common.cuh"
 
 namespace dimsum {
 namespace {
 
-constexpr int kRows = 128;   // threads per CTA == channel rows per CTA
-constexpr int kNS = 16;      // padded state count
-constexpr int kBCPitch = 20; // words; 16 states + pad -> conflict-free transposed STS.128 and aligned LDS.128
+constexpr int kRows = 128;          // threads per CTA == channel rows per CTA
+constexpr int kNS = 16;             // padded state count
+constexpr int kBCPitch = 20;        // words: 16 states + pad -> conflict-free transposed STS.128, aligned LDS.128
+constexpr int kRowBytes = 64;       // payload bytes per tile row per chunk
+constexpr int kRowPitch = 80;       // bytes; odd multiple of 16 -> conflict-free LDS.128 with one row per lane
 
 struct ScanFwdArgs {
     const void *u, *delta, *z, *B, *C;
@@ -30,19 +34,25 @@ struct ScanFwdArgs {
     const int32_t *perm;
     int64_t u_bs, u_ds, dl_bs, dl_ds, z_bs, z_ds, out_bs, out_ds, oz_bs, oz_ds;
     int64_t A_ds, A_ns, B_bs, B_gs, B_ns, C_bs, C_gs, C_ns;
-    int dim, seqlen, dstate, n_groups, n_chunks, chunk_len, softplus;
+    int dim, seqlen, dstate, n_groups, n_chunks, softplus, vec_io;
 };
 
 template <int LC>
 struct ScanSmem {
-    float dl[kRows][LC + 4];
-    float uy[kRows][LC + 4];
-    float Bs[LC][kBCPitch];
-    float Cs[LC][kBCPitch];
-    float bias[kRows];
+    unsigned char u[2][kRows][kRowPitch];
+    unsigned char dl[2][kRows][kRowPitch];
+    unsigned char z[2][kRows][kRowPitch];
+    float Bs[2][LC][kBCPitch];
+    float Cs[2][LC][kBCPitch];
 };
 
-// x[b][d][chunk][2n + slot]: slot 0 = h after 16 steps of the 32-step chunk, slot 1 = h after the chunk.
+DEV void cp_async16(void *smem, const void *gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::); }
+DEV void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// x[b][d][chunk32][2n + slot]: slot 0 = h after 16 steps of the 32-step chunk, slot 1 = h after the chunk.
 DEV void store_state(const ScanFwdArgs &a, int b, int d, int chunk, int slot, const float2 (&h2)[kNS / 2]) {
     float *xp = a.x + (((int64_t)b * a.dim + d) * a.n_chunks + chunk) * (2 * a.dstate) + slot;
 #pragma unroll
@@ -52,199 +62,217 @@ DEV void store_state(const ScanFwdArgs &a, int b, int d, int chunk, int slot, co
     }
 }
 
-template <typename T, int LC, bool kVecIO, bool kHasZ, int kPoly, int kPolyDeg>
-__global__ void __launch_bounds__(kRows, 4) scan_fwd_kernel(const ScanFwdArgs a) {
-    constexpr int VEC = Io<T>::kVec;
-    constexpr int VPR = LC / VEC;       // 16-byte vectors per row chunk
-    constexpr int RPP = kRows / VPR;    // rows covered per pass of the coalesced mapping
+template <typename T, bool kHasZ, int kPoly, int kPolyDeg>
+__global__ void __launch_bounds__(kRows, 3) scan_fwd_kernel(const ScanFwdArgs a) {
+    constexpr int VEC = Io<T>::kVec;                 // elements per 16 bytes
+    constexpr int LC = kRowBytes / (int)sizeof(T);   // steps per chunk: 16 (fp32) / 32 (16-bit)
+    constexpr int VPR = kRowBytes / 16;              // 16-byte vectors per tile row = 4
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ScanSmem<LC> &s = *reinterpret_cast<ScanSmem<LC> *>(smem_raw);
 
     const int tid = threadIdx.x;
     const int b = blockIdx.y;
-    const int dpg = a.dim / a.n_groups;                 // channels per group
+    const int dpg = a.dim / a.n_groups;
     const int slabs_per_group = (dpg + kRows - 1) / kRows;
     const int g = blockIdx.x / slabs_per_group;
     const int d0 = g * dpg + (blockIdx.x % slabs_per_group) * kRows;
-    const int nrows = min(kRows, (g + 1) * dpg - d0);   // valid rows of this slab
+    const int nrows = min(kRows, (g + 1) * dpg - d0);
     const int L = a.seqlen;
+    const bool row_ok = tid < nrows;
+    const bool gather = a.perm != nullptr;
 
     const T *u = reinterpret_cast<const T *>(a.u) + b * a.u_bs + (int64_t)d0 * a.u_ds;
     const T *dl = reinterpret_cast<const T *>(a.delta) + b * a.dl_bs + (int64_t)d0 * a.dl_ds;
+    const T *z = kHasZ ? reinterpret_cast<const T *>(a.z) + b * a.z_bs + (int64_t)d0 * a.z_ds : nullptr;
     const T *Bg = reinterpret_cast<const T *>(a.B) + b * a.B_bs + g * a.B_gs;
     const T *Cg = reinterpret_cast<const T *>(a.C) + b * a.C_bs + g * a.C_gs;
+    T *out = a.out != nullptr ? reinterpret_cast<T *>(a.out) + b * a.out_bs + (int64_t)d0 * a.out_ds : nullptr;
+    T *oz = kHasZ ? reinterpret_cast<T *>(a.out_z) + b * a.oz_bs + (int64_t)d0 * a.oz_ds : nullptr;
 
     // per-row constants of the scanning thread
-    const bool row_ok = tid < nrows;
     float2 A2[kNS / 2];
-    float Dv = 0.f;
+    float Dv = 0.f, bias = 0.f;
     {
         const float *Arow = a.A + (int64_t)(d0 + tid) * a.A_ds;
 #pragma unroll
         for (int p = 0; p < kNS / 2; ++p) {
-            float a0 = (row_ok && 2 * p < a.dstate) ? Arow[(2 * p) * a.A_ns] : 0.f;
-            float a1 = (row_ok && 2 * p + 1 < a.dstate) ? Arow[(2 * p + 1) * a.A_ns] : 0.f;
+            const float a0 = (row_ok && 2 * p < a.dstate) ? Arow[(2 * p) * a.A_ns] : 0.f;
+            const float a1 = (row_ok && 2 * p + 1 < a.dstate) ? Arow[(2 * p + 1) * a.A_ns] : 0.f;
             A2[p] = make_float2(a0 * kLog2e, a1 * kLog2e);
         }
         if (row_ok && a.D != nullptr) Dv = a.D[d0 + tid];
-        s.bias[tid] = (row_ok && a.delta_bias != nullptr) ? a.delta_bias[d0 + tid] : 0.f;
+        if (row_ok && a.delta_bias != nullptr) bias = a.delta_bias[d0 + tid];
     }
     float2 h2[kNS / 2];
 #pragma unroll
     for (int p = 0; p < kNS / 2; ++p) h2[p] = make_float2(0.f, 0.f);
-    __syncthreads();
 
     const int n_lc = (L + LC - 1) / LC;
-    for (int c = 0; c < n_lc; ++c) {
+
+    // ---- producers ---------------------------------------------------------------------------------------------
+    // tile fill for chunk c into stage st: 16-byte cp.async when everything is aligned, scalar copies otherwise
+    auto fill_tiles = [&](int c, int st) {
         const int l0 = c * LC;
-        // ---------------------------------------------------------------- (a) prep: global -> smem
-        if (kVecIO) {
-            const int vcol = tid % VPR, rsub = tid / VPR;
-            const bool col_ok = l0 + vcol * VEC < L;
+        if (a.vec_io) {
 #pragma unroll
-            for (int pass = 0; pass < VPR; ++pass) {
-                const int r = pass * RPP + rsub;
-                float uv[VEC], dv[VEC];
-                if (r < nrows && col_ok) {
-                    Io<T>::ldv(u + (int64_t)r * a.u_ds + l0 + vcol * VEC, uv);
-                    Io<T>::ldv(dl + (int64_t)r * a.dl_ds + l0 + vcol * VEC, dv);
-                    const float bias = s.bias[r];
-#pragma unroll
-                    for (int i = 0; i < VEC; ++i) {
-                        float d = dv[i] + bias;
-                        dv[i] = a.softplus ? softplus_f(d) : d;
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < VEC; ++i) { uv[i] = 0.f; dv[i] = 0.f; }
+            for (int i = 0; i < VPR; ++i) {
+                const int idx = tid + i * kRows;          // 0 .. kRows*VPR
+                const int r = idx / VPR, v = idx % VPR;
+                const int col = l0 + v * VEC;
+                if (r < nrows && col < L) {
+                    cp_async16(&s.u[st][r][v * 16], u + (int64_t)r * a.u_ds + col);
+                    cp_async16(&s.dl[st][r][v * 16], dl + (int64_t)r * a.dl_ds + col);
+                    if (kHasZ && !gather) cp_async16(&s.z[st][r][v * 16], z + (int64_t)r * a.z_ds + col);
                 }
-#pragma unroll
-                for (int i = 0; i < VEC; i += 4) {
-                    *reinterpret_cast<float4 *>(&s.dl[r][vcol * VEC + i]) = make_float4(dv[i], dv[i + 1], dv[i + 2], dv[i + 3]);
-                    *reinterpret_cast<float4 *>(&s.uy[r][vcol * VEC + i]) = make_float4(uv[i], uv[i + 1], uv[i + 2], uv[i + 3]);
+            }
+            if (kHasZ && gather) {
+                for (int idx = tid; idx < kRows * LC; idx += kRows) {
+                    const int r = idx / LC, col = idx % LC;
+                    if (r < nrows && l0 + col < L)
+                        reinterpret_cast<T *>(&s.z[st][r][0])[col] = z[(int64_t)r * a.z_ds + a.perm[l0 + col]];
                 }
             }
         } else {
             for (int idx = tid; idx < kRows * LC; idx += kRows) {
                 const int r = idx / LC, col = idx % LC;
-                float uv = 0.f, dv = 0.f;
                 if (r < nrows && l0 + col < L) {
-                    uv = Io<T>::ld(u + (int64_t)r * a.u_ds + l0 + col);
-                    float d = Io<T>::ld(dl + (int64_t)r * a.dl_ds + l0 + col) + s.bias[r];
-                    dv = a.softplus ? softplus_f(d) : d;
+                    reinterpret_cast<T *>(&s.u[st][r][0])[col] = u[(int64_t)r * a.u_ds + l0 + col];
+                    reinterpret_cast<T *>(&s.dl[st][r][0])[col] = dl[(int64_t)r * a.dl_ds + l0 + col];
+                    if (kHasZ) {
+                        const int tok = gather ? a.perm[l0 + col] : l0 + col;
+                        reinterpret_cast<T *>(&s.z[st][r][0])[col] = z[(int64_t)r * a.z_ds + tok];
+                    }
                 }
-                s.dl[r][col] = dv;
-                s.uy[r][col] = uv;
             }
         }
-        {   // B / C tile -> [l][n]; thread = (l = tid % LC, state quad = tid / LC) (+ strided for LC < 32)
-            for (int idx = tid; idx < LC * (kNS / 4); idx += kRows) {
-                const int l = idx % LC, nq = idx / LC;
-                float bv[4], cv[4];
+        cp_async_commit();
+    };
+    // B / C chunk through registers: thread = (l = tid % LC, state quad = tid / LC)
+    constexpr bool kBCAll = (LC * (kNS / 4) >= kRows);   // every thread participates (LC = 32)
+    const int bc_l = tid % LC, bc_q = tid / LC;
+    const bool bc_on = kBCAll || tid < LC * (kNS / 4);
+    float bq[4], cq[4];
+    auto load_bc = [&](int c) {
+        const int l = c * LC + bc_l;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int n = nq * 4 + i;
-                    const bool ok = n < a.dstate && l0 + l < L;
-                    bv[i] = ok ? Io<T>::ld(Bg + n * a.B_ns + l0 + l) : 0.f;
-                    cv[i] = ok ? Io<T>::ld(Cg + n * a.C_ns + l0 + l) : 0.f;
-                }
-                *reinterpret_cast<float4 *>(&s.Bs[l][nq * 4]) = make_float4(bv[0], bv[1], bv[2], bv[3]);
-                *reinterpret_cast<float4 *>(&s.Cs[l][nq * 4]) = make_float4(cv[0], cv[1], cv[2], cv[3]);
-            }
+        for (int i = 0; i < 4; ++i) {
+            const int n = bc_q * 4 + i;
+            const bool ok = bc_on && n < a.dstate && l < L;
+            bq[i] = ok ? Io<T>::ld(Bg + n * a.B_ns + l) : 0.f;
+            cq[i] = ok ? Io<T>::ld(Cg + n * a.C_ns + l) : 0.f;
         }
-        __syncthreads();
+    };
+    auto store_bc = [&](int st) {
+        if (bc_on) {
+            *reinterpret_cast<float4 *>(&s.Bs[st][bc_l][bc_q * 4]) = make_float4(bq[0], bq[1], bq[2], bq[3]);
+            *reinterpret_cast<float4 *>(&s.Cs[st][bc_l][bc_q * 4]) = make_float4(cq[0], cq[1], cq[2], cq[3]);
+        }
+    };
 
-        // ---------------------------------------------------------------- (b) recurrence, thread == row
+    fill_tiles(0, 0);
+    load_bc(0);
+    store_bc(0);
+
+    for (int c = 0; c < n_lc; ++c) {
+        const int st = c & 1;
+        const int l0 = c * LC;
+        cp_async_wait_all();
+        __syncthreads();                                   // chunk c landed for everybody; epilogue(c-1) finished
+        const bool more = c + 1 < n_lc;
+        if (more) {
+            fill_tiles(c + 1, st ^ 1);                     // streams in behind the recurrence below
+            load_bc(c + 1);
+        }
+
+        // ------------------------------------------------------------------------------ recurrence, thread == row
 #pragma unroll 1
-        for (int j = 0; j < LC; j += 4) {
-            const float4 d4 = *reinterpret_cast<const float4 *>(&s.dl[tid][j]);
-            const float4 u4 = *reinterpret_cast<const float4 *>(&s.uy[tid][j]);
-            const float ds[4] = {d4.x, d4.y, d4.z, d4.w};
-            const float us[4] = {u4.x, u4.y, u4.z, u4.w};
-            float ys[4];
+        for (int j = 0; j < LC; j += VEC) {
+            float dv[VEC], uv[VEC], zv[VEC], yv[VEC], gv[VEC];
+            Io<T>::ldv(reinterpret_cast<const T *>(&s.dl[st][tid][0]) + j, dv);
+            Io<T>::ldv(reinterpret_cast<const T *>(&s.u[st][tid][0]) + j, uv);
+            if (kHasZ) Io<T>::ldv(reinterpret_cast<const T *>(&s.z[st][tid][0]) + j, zv);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float dlt = ds[k];
-                const float du = dlt * us[k];
+            for (int k = 0; k < VEC; ++k) {
+                float dlt = dv[k] + bias;
+                if (a.softplus) dlt = softplus_f(dlt);
+                if (l0 + j + k >= L) {                     // identity step past the end keeps the final state exact
+                    dlt = 0.f;                             // (tile columns past L are never filled: do not trust them)
+                    uv[k] = 0.f;
+                }
+                const float du = dlt * uv[k];
                 float2 y2 = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int q = 0; q < kNS / 4; ++q) {
-                    const float4 Bq = *reinterpret_cast<const float4 *>(&s.Bs[j + k][q * 4]);
-                    const float4 Cq = *reinterpret_cast<const float4 *>(&s.Cs[j + k][q * 4]);
+                    const float4 Bq = *reinterpret_cast<const float4 *>(&s.Bs[st][j + k][q * 4]);
+                    const float4 Cq = *reinterpret_cast<const float4 *>(&s.Cs[st][j + k][q * 4]);
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
                         const int p = q * 2 + e;
                         const float2 Bp = e ? make_float2(Bq.z, Bq.w) : make_float2(Bq.x, Bq.y);
                         const float2 Cp = e ? make_float2(Cq.z, Cq.w) : make_float2(Cq.x, Cq.y);
-                        float2 t = mul2(splat2(dlt), A2[p]);
+                        const float2 t = mul2(splat2(dlt), A2[p]);
                         float2 dec;
                         if (p < kPoly) {
                             dec = ex2_poly2<kPolyDeg>(t);
                         } else {
                             dec = make_float2(ex2_mufu(t.x), ex2_mufu(t.y));
                         }
-                        const float2 drive = mul2(splat2(du), Bp);
-                        h2[p] = fma2(dec, h2[p], drive);
+                        h2[p] = fma2(dec, h2[p], mul2(splat2(du), Bp));
                         y2 = fma2(Cp, h2[p], y2);
                     }
                 }
-                ys[k] = fmaf(Dv, us[k], y2.x + y2.y);
+                yv[k] = fmaf(Dv, uv[k], y2.x + y2.y);
+                gv[k] = kHasZ ? yv[k] * silu_f(zv[k]) : yv[k];
             }
-            *reinterpret_cast<float4 *>(&s.uy[tid][j]) = make_float4(ys[0], ys[1], ys[2], ys[3]);
-            if (LC == 32 && j == 12 && a.x != nullptr && row_ok) store_state(a, b, d0 + tid, c, 0, h2);
+            // in place: gated output over u, pre-gate output (training only) over delta
+            Io<T>::stv(reinterpret_cast<T *>(&s.u[st][tid][0]) + j, gv);
+            if (kHasZ && out != nullptr) Io<T>::stv(reinterpret_cast<T *>(&s.dl[st][tid][0]) + j, yv);
+            if (a.x != nullptr && row_ok) {
+                const int done = l0 + j + VEC;             // steps completed (VEC divides 16)
+                if (done % 16 == 0) store_state(a, b, d0 + tid, (done - 1) / 32, (done % 32 == 0) ? 1 : 0, h2);
+            }
         }
-        // checkpoint for the backward / last_state: h after the chunk (slot 1; slot 0 was written mid-chunk)
-        if (a.x != nullptr && row_ok) store_state(a, b, d0 + tid, c, 1, h2);
-        __syncthreads();
+        if (more) store_bc(st ^ 1);
+        __syncthreads();                                   // outputs of chunk c visible
 
-        // ---------------------------------------------------------------- (c) epilogue: smem -> global
-        T *out = reinterpret_cast<T *>(a.out);
-        T *oz = reinterpret_cast<T *>(a.out_z);
-        const T *z = reinterpret_cast<const T *>(a.z);
-        if (kVecIO && a.perm == nullptr) {
-            const int vcol = tid % VPR, rsub = tid / VPR;
-            if (l0 + vcol * VEC < L) {
+        // ------------------------------------------------------------------------------ copy-out
+        // no z: the (ungated) result goes to `out`; with z: gated -> out_z and, when training, pre-gate -> out
+        T *dst_main = kHasZ ? oz : out;
+        const int64_t main_ds = kHasZ ? a.oz_ds : a.out_ds;
+        if (a.vec_io && !gather) {
 #pragma unroll
-                for (int pass = 0; pass < VPR; ++pass) {
-                    const int r = pass * RPP + rsub;
-                    if (r >= nrows) continue;
-                    float yv[VEC];
-#pragma unroll
-                    for (int i = 0; i < VEC; i += 4) {
-                        const float4 y4 = *reinterpret_cast<const float4 *>(&s.uy[r][vcol * VEC + i]);
-                        yv[i] = y4.x; yv[i + 1] = y4.y; yv[i + 2] = y4.z; yv[i + 3] = y4.w;
-                    }
-                    const int64_t col = l0 + vcol * VEC;
-                    if (out != nullptr) Io<T>::stv(out + b * a.out_bs + (int64_t)(d0 + r) * a.out_ds + col, yv);
-                    if (kHasZ) {
-                        float zv[VEC];
-                        Io<T>::ldv(z + b * a.z_bs + (int64_t)(d0 + r) * a.z_ds + col, zv);
-#pragma unroll
-                        for (int i = 0; i < VEC; ++i) yv[i] *= silu_f(zv[i]);
-                        Io<T>::stv(oz + b * a.oz_bs + (int64_t)(d0 + r) * a.oz_ds + col, yv);
-                    }
+            for (int i = 0; i < VPR; ++i) {
+                const int idx = tid + i * kRows;
+                const int r = idx / VPR, v = idx % VPR;
+                const int col = l0 + v * VEC;
+                if (r < nrows && col < L) {
+                    *reinterpret_cast<uint4 *>(dst_main + (int64_t)r * main_ds + col) =
+                        *reinterpret_cast<const uint4 *>(&s.u[st][r][v * 16]);
+                    if (kHasZ && out != nullptr)
+                        *reinterpret_cast<uint4 *>(out + (int64_t)r * a.out_ds + col) =
+                            *reinterpret_cast<const uint4 *>(&s.dl[st][r][v * 16]);
                 }
             }
         } else {
             for (int idx = tid; idx < kRows * LC; idx += kRows) {
                 const int r = idx / LC, col = idx % LC;
-                if (r >= nrows || l0 + col >= L) continue;
-                float y = s.uy[r][col];
-                if (out != nullptr) Io<T>::st(out + b * a.out_bs + (int64_t)(d0 + r) * a.out_ds + l0 + col, y);
-                if (kHasZ) {
-                    const int tok = a.perm != nullptr ? a.perm[l0 + col] : l0 + col;
-                    y *= silu_f(Io<T>::ld(z + b * a.z_bs + (int64_t)(d0 + r) * a.z_ds + tok));
-                    Io<T>::st(oz + b * a.oz_bs + (int64_t)(d0 + r) * a.oz_ds + tok, y);
+                if (r < nrows && l0 + col < L) {
+                    const int tok = (gather && kHasZ) ? a.perm[l0 + col] : l0 + col;
+                    dst_main[(int64_t)r * main_ds + tok] = reinterpret_cast<const T *>(&s.u[st][r][0])[col];
+                    if (kHasZ && out != nullptr)
+                        out[(int64_t)r * a.out_ds + l0 + col] = reinterpret_cast<const T *>(&s.dl[st][r][0])[col];
                 }
             }
         }
-        __syncthreads();
     }
+    // final state in slot 1 of the last 32-chunk even when L is not a multiple of 32
+    if (a.x != nullptr && row_ok) store_state(a, b, d0 + tid, (L - 1) / 32, 1, h2);
 }
 
-template <typename T, int LC, bool kVecIO, bool kHasZ, int kPoly, int kPolyDeg>
+template <typename T, bool kHasZ, int kPoly, int kPolyDeg>
 int launch(const ScanFwdArgs &a, int batch, cudaStream_t stream) {
-    auto kern = scan_fwd_kernel<T, LC, kVecIO, kHasZ, kPoly, kPolyDeg>;
+    constexpr int LC = kRowBytes / (int)sizeof(T);
+    auto kern = scan_fwd_kernel<T, kHasZ, kPoly, kPolyDeg>;
     const int smem = (int)sizeof(ScanSmem<LC>);
     static bool configured = false;   // per instantiation
     if (!configured) {
@@ -257,15 +285,29 @@ int launch(const ScanFwdArgs &a, int batch, cudaStream_t stream) {
     return check_launch("selective_scan_fwd");
 }
 
-template <typename T, int kPoly, int kPolyDeg>
-int dispatch(const ScanFwdArgs &a, int batch, bool vec_ok, cudaStream_t stream) {
+template <typename T, int kPolyDeg>
+int dispatch(const ScanFwdArgs &a, int batch, int poly, cudaStream_t stream) {
     const bool has_z = a.z != nullptr;
-    if (vec_ok) {
-        return has_z ? launch<T, 32, true, true, kPoly, kPolyDeg>(a, batch, stream)
-                     : launch<T, 32, true, false, kPoly, kPolyDeg>(a, batch, stream);
-    }
-    return has_z ? launch<T, 32, false, true, kPoly, kPolyDeg>(a, batch, stream)
-                 : launch<T, 32, false, false, kPoly, kPolyDeg>(a, batch, stream);
+#define DIMSUM_SCAN_CASE(P)                                                            \
+    if (poly == P)                                                                     \
+        return has_z ? launch<T, true, P, kPolyDeg>(a, batch, stream) : launch<T, false, P, kPolyDeg>(a, batch, stream);
+    DIMSUM_SCAN_CASE(0)
+    DIMSUM_SCAN_CASE(2)
+    DIMSUM_SCAN_CASE(3)
+    DIMSUM_SCAN_CASE(4)
+#undef DIMSUM_SCAN_CASE
+    return fail(DIMSUM_ERR_INVALID, "selective_scan_fwd: unsupported poly split %d", poly);
+}
+
+int poly_pairs(int io_dtype) {
+    // developer knob (tools/bench_ops.py sweeps it); default chosen from measurements recorded in profiles/
+    static int env = [] {
+        const char *e = getenv("DIMSUM_SCAN_POLY");
+        return e ? atoi(e) : -1;
+    }();
+    if (env >= 0) return env;
+    (void)io_dtype;
+    return 0;
 }
 
 }  // namespace
@@ -289,10 +331,12 @@ extern "C" int dimsum_selective_scan_fwd(const dimsum_scan_fwd_params *p, void *
                    "selective_scan_fwd: z and out_z must be given together");
     DIMSUM_REQUIRE(p->out != nullptr || p->out_z != nullptr, DIMSUM_ERR_INVALID, "selective_scan_fwd: no output buffer");
     DIMSUM_REQUIRE(p->perm == nullptr || p->z != nullptr, DIMSUM_ERR_INVALID, "selective_scan_fwd: perm needs z/out_z");
+    DIMSUM_REQUIRE(p->io_dtype >= 0 && p->io_dtype <= 2, DIMSUM_ERR_INVALID, "selective_scan_fwd: unknown io_dtype %lld",
+                   (long long)p->io_dtype);
     if (p->x != nullptr) {
         DIMSUM_REQUIRE(p->chunk_len == 32, DIMSUM_ERR_INVALID, "selective_scan_fwd: chunk_len must be 32");
-        DIMSUM_REQUIRE(p->n_chunks == (p->seqlen + p->chunk_len - 1) / p->chunk_len, DIMSUM_ERR_INVALID,
-                       "selective_scan_fwd: n_chunks does not match seqlen / chunk_len");
+        DIMSUM_REQUIRE(p->n_chunks == (p->seqlen + 31) / 32, DIMSUM_ERR_INVALID,
+                       "selective_scan_fwd: n_chunks must be ceil(seqlen / 32)");
     }
     DIMSUM_REQUIRE(p->batch <= 65535, DIMSUM_ERR_UNSUPPORTED, "selective_scan_fwd: batch > 65535");
     if (p->batch == 0) return DIMSUM_OK;
@@ -312,7 +356,7 @@ extern "C" int dimsum_selective_scan_fwd(const dimsum_scan_fwd_params *p, void *
     a.B_bs = p->B_batch_stride; a.B_gs = p->B_group_stride; a.B_ns = p->B_dstate_stride;
     a.C_bs = p->C_batch_stride; a.C_gs = p->C_group_stride; a.C_ns = p->C_dstate_stride;
     a.dim = (int)p->dim; a.seqlen = (int)p->seqlen; a.dstate = (int)p->dstate; a.n_groups = (int)p->n_groups;
-    a.n_chunks = (int)p->n_chunks; a.chunk_len = (int)(p->chunk_len > 0 ? p->chunk_len : 2048);
+    a.n_chunks = (int)p->n_chunks;
     a.softplus = p->delta_softplus != 0;
 
     const int esz = p->io_dtype == DIMSUM_F32 ? 4 : 2;
@@ -322,11 +366,12 @@ extern "C" int dimsum_selective_scan_fwd(const dimsum_scan_fwd_params *p, void *
                   strides_ok(a.dl_bs, a.dl_ds);
     if (p->out) vec_ok = vec_ok && aligned16(p->out) && strides_ok(a.out_bs, a.out_ds);
     if (p->z) vec_ok = vec_ok && aligned16(p->z) && aligned16(p->out_z) && strides_ok(a.z_bs, a.z_ds) && strides_ok(a.oz_bs, a.oz_ds);
+    a.vec_io = vec_ok;
 
+    const int poly = poly_pairs((int)p->io_dtype);
     switch (p->io_dtype) {
-        case DIMSUM_F32: return dispatch<float, 0, 5>(a, (int)p->batch, vec_ok, stream);
-        case DIMSUM_BF16: return dispatch<__nv_bfloat16, 0, 3>(a, (int)p->batch, vec_ok, stream);
-        case DIMSUM_F16: return dispatch<__half, 0, 3>(a, (int)p->batch, vec_ok, stream);
-        default: return fail(DIMSUM_ERR_INVALID, "selective_scan_fwd: unknown io_dtype %lld", (long long)p->io_dtype);
+        case DIMSUM_F32: return dispatch<float, 5>(a, (int)p->batch, poly, stream);
+        case DIMSUM_BF16: return dispatch<__nv_bfloat16, 3>(a, (int)p->batch, poly, stream);
+        default: return dispatch<__half, 3>(a, (int)p->batch, poly, stream);
     }
 }

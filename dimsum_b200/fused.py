@@ -1,0 +1,92 @@
+"""Inference-time fused glue around the mixer: adaLN modulate, gated residual (both with the token order folded into the
+row index) and residual-add + RMSNorm.  Reference: `modulate` dimsum/models_dim.py:34-35, the gated residuals
+:1510-1512 / :686-689, the transpose / flip copies :1498-1524, and the Triton `rms_norm_fn`
+(mamba/mamba_ssm/ops/triton/layernorm.py:460).  One coalesced pass each; no permuted copy is materialised.
+These have no autograd: the model uses them when gradients are off (sampling) and plain torch ops when training.
+"""
+import torch
+
+from . import _lib
+
+_DT = {torch.float32: _lib.DTYPE_F32, torch.float16: _lib.DTYPE_F16, torch.bfloat16: _lib.DTYPE_BF16}
+
+
+def _rows(t, name):
+    if t.dim() != 3 or t.stride(2) != 1 or not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA (batch, seqlen, channels) tensor with channel stride 1")
+
+
+def _vec(t, ref, name):
+    if t.dim() != 2 or t.stride(1) != 1 or t.shape != (ref.shape[0], ref.shape[2]) or t.dtype != ref.dtype:
+        raise RuntimeError(f"{name} must be (batch, channels) with stride(1) == 1 and the dtype of x")
+
+
+def _idx(idx, L):
+    if idx is None:
+        return None
+    if idx.dtype != torch.int32 or not idx.is_cuda or idx.numel() != L or not idx.is_contiguous():
+        raise RuntimeError("idx must be a contiguous int32 CUDA tensor of length seqlen")
+    return idx.data_ptr()
+
+
+def modulate(x, shift, scale, idx=None):
+    """out[b, l] = x[b, idx[l]] * (1 + scale[b]) + shift[b]"""
+    _rows(x, "x"); _vec(shift, x, "shift"); _vec(scale, x, "scale")
+    if shift.stride(0) != scale.stride(0):
+        raise RuntimeError("shift and scale must share their row stride (chunks of one adaLN output)")
+    out = torch.empty(x.shape, device=x.device, dtype=x.dtype)
+    with torch.cuda.device(x.device):
+        p = _lib.RowwiseParams()
+        p.batch, p.seqlen, p.channels, p.dtype = x.shape[0], x.shape[1], x.shape[2], _DT[x.dtype]
+        p.x_batch_stride, p.x_token_stride = x.stride(0), x.stride(1)
+        p.dst_batch_stride, p.dst_token_stride = out.stride(0), out.stride(1)
+        p.vec_row_stride = shift.stride(0)
+        p.x, p.shift, p.scale, p.dst = x.data_ptr(), shift.data_ptr(), scale.data_ptr(), out.data_ptr()
+        p.idx = _idx(idx, x.shape[1])
+        _lib.call("dimsum_modulate", p, torch.cuda.current_stream(x.device).cuda_stream)
+    return out
+
+
+def gate_residual(x, gate, m, idx=None):
+    """out[b, l] = x[b, l] + gate[b] * m[b, idx[l]]"""
+    _rows(x, "x"); _rows(m, "m"); _vec(gate, x, "gate")
+    if m.shape != x.shape or m.dtype != x.dtype:
+        raise RuntimeError("m must match x")
+    out = torch.empty(x.shape, device=x.device, dtype=x.dtype)
+    with torch.cuda.device(x.device):
+        p = _lib.RowwiseParams()
+        p.batch, p.seqlen, p.channels, p.dtype = x.shape[0], x.shape[1], x.shape[2], _DT[x.dtype]
+        p.x_batch_stride, p.x_token_stride = x.stride(0), x.stride(1)
+        p.m_batch_stride, p.m_token_stride = m.stride(0), m.stride(1)
+        p.dst_batch_stride, p.dst_token_stride = out.stride(0), out.stride(1)
+        p.vec_row_stride = gate.stride(0)
+        p.x, p.m, p.gate, p.dst = x.data_ptr(), m.data_ptr(), gate.data_ptr(), out.data_ptr()
+        p.idx = _idx(idx, x.shape[1])
+        _lib.call("dimsum_gate_residual", p, torch.cuda.current_stream(x.device).cuda_stream)
+    return out
+
+
+def add_rmsnorm(x, residual, weight, eps, want_residual=True):
+    """-> (y, res_out): res_out = x + residual in fp32, y = rmsnorm(res_out) * weight in x.dtype."""
+    shape = x.shape
+    x2 = x.reshape(-1, shape[-1])
+    if x2.stride(1) != 1:
+        x2 = x2.contiguous()
+    rows, C = x2.shape
+    if residual is not None:
+        if residual.dtype != torch.float32 or residual.shape != shape:
+            raise RuntimeError("add_rmsnorm: residual must be fp32 with the shape of x")
+        residual = residual.contiguous()
+    w = weight.float().contiguous()
+    y = torch.empty((rows, C), device=x.device, dtype=x.dtype)
+    res_out = torch.empty((rows, C), device=x.device, dtype=torch.float32) if want_residual else None
+    with torch.cuda.device(x.device):
+        p = _lib.RmsnormParams()
+        p.rows, p.channels, p.dtype = rows, C, _DT[x.dtype]
+        p.x_row_stride, p.y_row_stride = x2.stride(0), y.stride(0)
+        p.x, p.weight, p.y = x2.data_ptr(), w.data_ptr(), y.data_ptr()
+        p.residual = residual.data_ptr() if residual is not None else None
+        p.res_out = res_out.data_ptr() if res_out is not None else None
+        p.eps = eps
+        _lib.call("dimsum_add_rmsnorm", p, torch.cuda.current_stream(x.device).cuda_stream)
+    return y.view(shape), (res_out.view(shape) if res_out is not None else None)

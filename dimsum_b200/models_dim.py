@@ -23,6 +23,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import fused
 from . import scanning_orders as so
 from .mamba_simple import CondMamba
 from .wavelet import wavelet_packet, wavelet_packet_inverse
@@ -30,6 +31,25 @@ from .wavelet import wavelet_packet, wavelet_packet_inverse
 
 def modulate(x, shift, scale):
     return x * (1 + scale.unsqueeze(1)) + shift.unsqueeze(1)
+
+
+def _fused_ok(x):
+    """The one-pass CUDA glue kernels have no autograd: use them exactly when nothing is being recorded."""
+    return x.is_cuda and not torch.is_grad_enabled()
+
+
+def _mod(x, shift, scale, idx=None):
+    if _fused_ok(x):
+        return fused.modulate(x, shift.to(x.dtype), scale.to(x.dtype), idx)
+    assert idx is None
+    return modulate(x, shift, scale)
+
+
+def _gated(x, gate, m, idx=None):
+    if _fused_ok(x):
+        return fused.gate_residual(x, gate.to(x.dtype), m.to(x.dtype), idx)
+    assert idx is None
+    return x + gate.unsqueeze(1) * m
 
 
 class RMSNorm(nn.Module):
@@ -43,6 +63,9 @@ class RMSNorm(nn.Module):
         self.register_parameter("bias", None)
 
     def forward(self, x, residual=None, prenorm=False, residual_in_fp32=False):
+        if _fused_ok(x) and (residual is None or residual.dtype == torch.float32) and (residual_in_fp32 or not prenorm):
+            y, res = fused.add_rmsnorm(x, residual, self.weight, self.eps, want_residual=prenorm)
+            return (y, res) if prenorm else y
         io_dtype = x.dtype
         xf = x.float()
         if residual is not None:
@@ -161,9 +184,15 @@ class DiMBlockRaw(nn.Module):
         self.adaLN_modulation = nn.Sequential(nn.SiLU(), nn.Linear(c_dim, 3 * dim, bias=True))
         order = so.implicit_order(grid, transpose, reverse) if (reverse or transpose) else None
         self.register_buffer("_order", _order_buffer(order) if order is not None else None, persistent=False)
+        self.register_buffer("_inv", _order_buffer(so.reverse_permut_np(order)) if order is not None else None,
+                             persistent=False)
 
     def forward(self, x, c):
         shift, scale, gate = self.adaLN_modulation(c).chunk(3, dim=1)
+        if _fused_ok(x):
+            # the scan order rides on the row index of the two glue kernels: no permuted copy, no extra pass
+            m = self.mixer(_mod(x, shift, scale, self._order), c)
+            return _gated(x, gate, m, self._inv)
         return x + gate.unsqueeze(1) * self.mixer(modulate(x, shift, scale), c, order=self._order)
 
 
@@ -190,7 +219,7 @@ class WaveDiMBlock(nn.Module):
     def forward(self, x, c):
         h = wavelet_packet(x, self._pos)                                 # _dwt_fast + local_scan
         shift, scale, gate = self.adaLN_modulation(c).chunk(3, dim=1)
-        h = h + gate.unsqueeze(1) * self.mixer(modulate(h, shift, scale), c)
+        h = _gated(h, gate, self.mixer(_mod(h, shift, scale), c))
         return wavelet_packet_inverse(h, self._pos)                      # local_reverse + _idwt_fast
 
 
@@ -211,7 +240,7 @@ class DiMBlockCombined(nn.Module):
         x = self.proj(self.spatial_mamba(x1, c), self.freq_mamba(x2, c))
         hidden_states = hidden_states + x
         shift, scale, gate = self.adaLN_modulation(c).chunk(3, dim=1)
-        hidden_states = hidden_states + gate.unsqueeze(1) * self.mlp(modulate(self.norm_2(hidden_states), shift, scale))
+        hidden_states = _gated(hidden_states, gate, self.mlp(_mod(self.norm_2(hidden_states), shift, scale)))
         return hidden_states, residual
 
 
@@ -226,8 +255,8 @@ class DiTBlock(nn.Module):
 
     def forward(self, x, c):
         s1, sc1, g1, s2, sc2, g2 = self.adaLN_modulation(c).chunk(6, dim=1)
-        x = x + g1.unsqueeze(1) * self.attn(modulate(self.norm1(x), s1, sc1))
-        return x + g2.unsqueeze(1) * self.mlp(modulate(self.norm2(x), s2, sc2))
+        x = _gated(x, g1, self.attn(_mod(self.norm1(x), s1, sc1)))
+        return _gated(x, g2, self.mlp(_mod(self.norm2(x), s2, sc2)))
 
 
 class FinalLayer(nn.Module):
@@ -239,7 +268,7 @@ class FinalLayer(nn.Module):
 
     def forward(self, x, c):
         shift, scale = self.adaLN_modulation(c).chunk(2, dim=1)
-        return self.linear(modulate(self.norm_final(x), shift, scale))
+        return self.linear(_mod(self.norm_final(x), shift, scale))
 
 
 def get_2d_sincos_pos_embed(embed_dim, grid_size):

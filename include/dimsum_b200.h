@@ -18,6 +18,9 @@
  *                               rearrange/flip/local_scan copies of dimsum/models_dim.py:1498-1524, :660-664,:700-701
  *   dimsum_wavelet_packet_fwd   WaveDiMBlock._dwt_fast  dimsum/models_dim.py:572-586 (+ local_scan :662)
  *   dimsum_wavelet_packet_inv   WaveDiMBlock._idwt_fast dimsum/models_dim.py:588-604 (+ local_reverse :701)
+ *   dimsum_modulate / dimsum_gate_residual / dimsum_add_rmsnorm
+ *                               the adaLN modulate, gated residual and fused add+RMSNorm passes around every mixer call
+ *                               (models_dim.py:34-35,1079-1098,1509-1512; layernorm.py:460), with the token order folded in
  *
  * All strides are in ELEMENTS of the tensor's own dtype.  The innermost (sequence) stride of every
  * (batch, dim, seqlen) tensor is 1, as the reference requires (selective_scan.cpp:252-253).
@@ -174,6 +177,40 @@ typedef struct {
 
 int dimsum_wavelet_packet_fwd(const dimsum_wavelet_params *p, void *stream);
 int dimsum_wavelet_packet_inv(const dimsum_wavelet_params *p, void *stream);
+
+/* ---- token-major elementwise glue around the mixer, with the token order folded in ----------
+ * modulate      : dst[b, l, :] = x[b, idx[l], :] * (1 + scale[b, :]) + shift[b, :]          (models_dim.py:34-35 + order)
+ * gate_residual : dst[b, l, :] = x[b, l, :] + gate[b, :] * m[b, idx[l], :]                  (models_dim.py:1510-1512 + un-order)
+ * x, m, dst: (batch, seqlen, channels) with channel stride 1; shift/scale/gate: (batch, channels) with a row stride
+ * (they are chunks of one adaLN GEMM output).  idx: NULL or int32[seqlen].  All tensors share `dtype`.
+ */
+typedef struct {
+    int64_t batch, seqlen, channels, dtype;
+    int64_t x_batch_stride, x_token_stride;
+    int64_t m_batch_stride, m_token_stride;
+    int64_t dst_batch_stride, dst_token_stride;
+    int64_t vec_row_stride;                  /* row stride of shift / scale / gate */
+    const void *x, *m, *shift, *scale, *gate;
+    const int32_t *idx;
+    void *dst;
+} dimsum_rowwise_params;
+
+int dimsum_modulate(const dimsum_rowwise_params *p, void *stream);
+int dimsum_gate_residual(const dimsum_rowwise_params *p, void *stream);
+
+/* residual-add + RMSNorm (reference: Triton _layer_norm_fwd_1pass_kernel, mamba_ssm/ops/triton/layernorm.py:62-118,
+ * maths of rms_norm_ref :32-47): res_out = x + residual (fp32), y = res_out * rsqrt(mean(res_out^2) + eps) * weight.
+ * x: (rows, channels) `dtype`; residual / res_out: fp32 or NULL; weight fp32; y `dtype`.
+ */
+typedef struct {
+    int64_t rows, channels, dtype;
+    int64_t x_row_stride, y_row_stride;
+    const void *x, *residual, *weight;
+    void *y, *res_out;
+    float eps;
+} dimsum_rmsnorm_params;
+
+int dimsum_add_rmsnorm(const dimsum_rmsnorm_params *p, void *stream);
 
 /* ---- misc --------------------------------------------------------------------------------- */
 int dimsum_abi_version(void);

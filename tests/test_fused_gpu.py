@@ -1,0 +1,45 @@
+"""GPU parity of the inference glue kernels (modulate / gated residual with folded token order, add + RMSNorm)."""
+import pytest
+import torch
+
+from golden_io import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_modulate_and_gate_residual_with_order(dtype):
+    from dimsum_b200 import fused, scanning_orders as so
+    g = torch.Generator(device="cuda").manual_seed(0)
+    R, L, C = 5, 256, 512
+    hidden = torch.randn(R, L, 2 * C, generator=g, device="cuda").to(dtype)
+    x = hidden[:, :, C:]                                                   # strided half, like x2 = hidden.chunk(2, dim=2)[1]
+    ada = torch.randn(R, 3 * C, generator=g, device="cuda").to(dtype)
+    shift, scale, gate = ada.chunk(3, dim=1)
+    order = torch.from_numpy(so.implicit_order(16, True, True)).cuda()
+    inv = torch.from_numpy(so.reverse_permut_np(order.cpu().numpy())).cuda()
+    want = (x.float() * (1 + scale.float().unsqueeze(1)) + shift.float().unsqueeze(1))[:, order]
+    got = fused.modulate(x, shift, scale, order.to(torch.int32))
+    assert rel_err(got, want) <= (1e-6 if dtype == torch.float32 else 1e-2)
+    m = torch.randn(R, L, C, generator=g, device="cuda").to(dtype)
+    want = x.float() + gate.float().unsqueeze(1) * m.float()[:, inv]
+    got = fused.gate_residual(x, gate, m, inv.to(torch.int32))
+    assert rel_err(got, want) <= (1e-6 if dtype == torch.float32 else 1e-2)
+    assert torch.equal(fused.modulate(x, shift, scale), fused.modulate(x.contiguous(), shift, scale))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("C", [64, 1024])
+def test_add_rmsnorm_matches_oracle(dtype, C):
+    from dimsum_b200 import fused
+    from oracle import ref_ops
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(3, 50, C, generator=g).to(dtype)
+    res = torch.randn(3, 50, C, generator=g)
+    w = 1 + 0.1 * torch.randn(C, generator=g)
+    want_y, want_res = ref_ops.rms_norm_oracle(x, w, residual=res, eps=1e-5, prenorm=True)
+    y, r = fused.add_rmsnorm(x.cuda(), res.cuda(), w.cuda(), 1e-5)
+    assert rel_err(y, want_y) <= (2e-6 if dtype == torch.float32 else 1e-2)
+    assert rel_err(r, want_res) <= 1e-6
+    y2, none = fused.add_rmsnorm(x.cuda(), None, w.cuda(), 1e-5, want_residual=False)
+    assert none is None and rel_err(y2, ref_ops.rms_norm_oracle(x, w, eps=1e-5)) <= (2e-6 if dtype == torch.float32 else 1e-2)
