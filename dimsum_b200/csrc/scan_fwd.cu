@@ -15,6 +15,8 @@
 //     as warp-wide 128-bit broadcasts: B and C are fetched once per 128 channels, not once per channel as in the reference;
 //   * kPoly of the 8 state pairs evaluate 2^x as a Cody-Waite polynomial on the FMA pipe instead of MUFU.EX2, because at
 //     16 SFU lanes/clk/SM the exp unit -- not HBM -- is the first limiter of this kernel.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace dimsum {
@@ -62,7 +64,7 @@ DEV void store_state(const ScanFwdArgs &a, int b, int d, int chunk, int slot, co
     }
 }
 
-template <typename T, bool kHasZ, int kPoly, int kPolyDeg>
+template <typename T, bool kHasZ, bool kSoftplus, int kPoly, int kPolyDeg>
 __global__ void __launch_bounds__(kRows, 3) scan_fwd_kernel(const ScanFwdArgs a) {
     constexpr int VEC = Io<T>::kVec;                 // elements per 16 bytes
     constexpr int LC = kRowBytes / (int)sizeof(T);   // steps per chunk: 16 (fp32) / 32 (16-bit)
@@ -185,22 +187,29 @@ __global__ void __launch_bounds__(kRows, 3) scan_fwd_kernel(const ScanFwdArgs a)
         }
 
         // ------------------------------------------------------------------------------ recurrence, thread == row
-#pragma unroll 1
-        for (int j = 0; j < LC; j += VEC) {
+        // One branch-free basic block per 16-byte group of steps, so ptxas can interleave the independent softplus /
+        // exp / FMA chains of the VEC steps; the ragged tail (l >= L) takes a masked copy of the same body.
+        auto group = [&](int j, auto masked) {
+            constexpr bool kMask = decltype(masked)::value;
             float dv[VEC], uv[VEC], zv[VEC], yv[VEC], gv[VEC];
             Io<T>::ldv(reinterpret_cast<const T *>(&s.dl[st][tid][0]) + j, dv);
             Io<T>::ldv(reinterpret_cast<const T *>(&s.u[st][tid][0]) + j, uv);
             if (kHasZ) Io<T>::ldv(reinterpret_cast<const T *>(&s.z[st][tid][0]) + j, zv);
 #pragma unroll
             for (int k = 0; k < VEC; ++k) {
-                float dlt = dv[k] + bias;
-                if (a.softplus) dlt = softplus_f(dlt);
-                if (l0 + j + k >= L) {                     // identity step past the end keeps the final state exact
-                    dlt = 0.f;                             // (tile columns past L are never filled: do not trust them)
+                dv[k] += bias;
+                if (kSoftplus) dv[k] = softplus_f(dv[k]);
+                if (kMask && l0 + j + k >= L) {            // identity step past the end keeps the final state exact
+                    dv[k] = 0.f;                           // (tile columns past L are never filled: do not trust them)
                     uv[k] = 0.f;
+                    if (kHasZ) zv[k] = 0.f;
                 }
+            }
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+                const float dlt = dv[k];
                 const float du = dlt * uv[k];
-                float2 y2 = make_float2(0.f, 0.f);
+                float2 ya = make_float2(0.f, 0.f), yb = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int q = 0; q < kNS / 4; ++q) {
                     const float4 Bq = *reinterpret_cast<const float4 *>(&s.Bs[st][j + k][q * 4]);
@@ -218,18 +227,30 @@ __global__ void __launch_bounds__(kRows, 3) scan_fwd_kernel(const ScanFwdArgs a)
                             dec = make_float2(ex2_mufu(t.x), ex2_mufu(t.y));
                         }
                         h2[p] = fma2(dec, h2[p], mul2(splat2(du), Bp));
-                        y2 = fma2(Cp, h2[p], y2);
+                        if (e) yb = fma2(Cp, h2[p], yb); else ya = fma2(Cp, h2[p], ya);
                     }
                 }
+                const float2 y2 = add2(ya, yb);
                 yv[k] = fmaf(Dv, uv[k], y2.x + y2.y);
                 gv[k] = kHasZ ? yv[k] * silu_f(zv[k]) : yv[k];
             }
             // in place: gated output over u, pre-gate output (training only) over delta
             Io<T>::stv(reinterpret_cast<T *>(&s.u[st][tid][0]) + j, gv);
             if (kHasZ && out != nullptr) Io<T>::stv(reinterpret_cast<T *>(&s.dl[st][tid][0]) + j, yv);
-            if (a.x != nullptr && row_ok) {
-                const int done = l0 + j + VEC;             // steps completed (VEC divides 16)
-                if (done % 16 == 0) store_state(a, b, d0 + tid, (done - 1) / 32, (done % 32 == 0) ? 1 : 0, h2);
+        };
+        const bool tail = l0 + LC > L;
+#pragma unroll 1
+        for (int half = 0; half < LC / 16; ++half) {
+            if (!tail) {
+#pragma unroll 1
+                for (int j = half * 16; j < half * 16 + 16; j += VEC) group(j, std::false_type{});
+            } else {
+#pragma unroll 1
+                for (int j = half * 16; j < half * 16 + 16; j += VEC) group(j, std::true_type{});
+            }
+            if (a.x != nullptr && row_ok) {                // 16-step checkpoints for the backward
+                const int done = l0 + half * 16 + 16;
+                store_state(a, b, d0 + tid, (done - 1) / 32, (done % 32 == 0) ? 1 : 0, h2);
             }
         }
         if (more) store_bc(st ^ 1);
@@ -269,10 +290,10 @@ __global__ void __launch_bounds__(kRows, 3) scan_fwd_kernel(const ScanFwdArgs a)
     if (a.x != nullptr && row_ok) store_state(a, b, d0 + tid, (L - 1) / 32, 1, h2);
 }
 
-template <typename T, bool kHasZ, int kPoly, int kPolyDeg>
+template <typename T, bool kHasZ, bool kSoftplus, int kPoly, int kPolyDeg>
 int launch(const ScanFwdArgs &a, int batch, cudaStream_t stream) {
     constexpr int LC = kRowBytes / (int)sizeof(T);
-    auto kern = scan_fwd_kernel<T, kHasZ, kPoly, kPolyDeg>;
+    auto kern = scan_fwd_kernel<T, kHasZ, kSoftplus, kPoly, kPolyDeg>;
     const int smem = (int)sizeof(ScanSmem<LC>);
     static bool configured = false;   // per instantiation
     if (!configured) {
@@ -285,17 +306,20 @@ int launch(const ScanFwdArgs &a, int batch, cudaStream_t stream) {
     return check_launch("selective_scan_fwd");
 }
 
+template <typename T, int kPoly, int kPolyDeg>
+int dispatch2(const ScanFwdArgs &a, int batch, cudaStream_t stream) {
+    if (a.z != nullptr) {
+        return a.softplus ? launch<T, true, true, kPoly, kPolyDeg>(a, batch, stream)
+                          : launch<T, true, false, kPoly, kPolyDeg>(a, batch, stream);
+    }
+    return a.softplus ? launch<T, false, true, kPoly, kPolyDeg>(a, batch, stream)
+                      : launch<T, false, false, kPoly, kPolyDeg>(a, batch, stream);
+}
+
 template <typename T, int kPolyDeg>
 int dispatch(const ScanFwdArgs &a, int batch, int poly, cudaStream_t stream) {
-    const bool has_z = a.z != nullptr;
-#define DIMSUM_SCAN_CASE(P)                                                            \
-    if (poly == P)                                                                     \
-        return has_z ? launch<T, true, P, kPolyDeg>(a, batch, stream) : launch<T, false, P, kPolyDeg>(a, batch, stream);
-    DIMSUM_SCAN_CASE(0)
-    DIMSUM_SCAN_CASE(2)
-    DIMSUM_SCAN_CASE(3)
-    DIMSUM_SCAN_CASE(4)
-#undef DIMSUM_SCAN_CASE
+    if (poly == 0) return dispatch2<T, 0, kPolyDeg>(a, batch, stream);
+    if (poly == 2) return dispatch2<T, 2, kPolyDeg>(a, batch, stream);
     return fail(DIMSUM_ERR_INVALID, "selective_scan_fwd: unsupported poly split %d", poly);
 }
 

@@ -45,6 +45,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--json", default=None)
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--bwd", action="store_true", help="time the backward kernels at every shape (default: R <= 64)")
     args = ap.parse_args()
     from dimsum_b200 import causal_conv1d_cuda, selective_scan_cuda, wavelet_packet, scanning_orders as so
     pk = peak()
@@ -82,6 +83,19 @@ def main():
             med, best = timeit(lambda: causal_conv1d_cuda.causal_conv1d_fwd(u, w, cb, True), flush=flush)
             rows.append(dict(op="conv_fwd", dtype=str(dtype), R=R, D=D, L=L, ms=med, ms_best=best, gbs=by_c / med / 1e6,
                              frac=by_c / med / 1e6 / pk))
+            if R <= 64 or args.bwd:
+                out, xck, out_z = selective_scan_cuda.fwd(u, delta, A, Bm, Cm, Dv, z, bias, True)
+                dout = torch.randn(R, D, L, generator=g, device="cuda").to(dtype)
+                by_b = s * (9 * R * D * L + 2 * R * N * L) + 4 * 2 * R * N * L + 4 * R * D * ((L + 31) // 32) * 2 * N
+                med, best = timeit(lambda: selective_scan_cuda.bwd(u, delta, A, Bm, Cm, Dv, z, bias, dout, xck, out, None, True, True),
+                                   flush=flush)
+                rows.append(dict(op="scan_bwd", dtype=str(dtype), R=R, D=D, L=L, ms=med, ms_best=best, gbs=by_b / med / 1e6,
+                                 frac=by_b / med / 1e6 / pk))
+                by_cb = 3 * s * R * D * L
+                med, best = timeit(lambda: causal_conv1d_cuda.causal_conv1d_bwd(u, w, cb, dout, None, True), flush=flush)
+                rows.append(dict(op="conv_bwd", dtype=str(dtype), R=R, D=D, L=L, ms=med, ms_best=best, gbs=by_cb / med / 1e6,
+                                 frac=by_cb / med / 1e6 / pk))
+                del out, xck, out_z, dout
             del xz, u, z, delta, Bm, Cm
         # wavelet at the model shape: 512 rows, 16x16 tokens, 512 channels
         x = torch.randn(512, 256, 512, device="cuda").to(dtype)
