@@ -112,6 +112,7 @@ GatherParams = STRUCTS["dimsum_gather_params"]
 WaveletParams = STRUCTS["dimsum_wavelet_params"]
 RowwiseParams = STRUCTS["dimsum_rowwise_params"]
 RmsnormParams = STRUCTS["dimsum_rmsnorm_params"]
+GeluMulParams = STRUCTS["dimsum_gelu_mul_params"]
 
 ENTRY_POINTS = {
     "dimsum_selective_scan_fwd": ScanFwdParams,
@@ -124,6 +125,7 @@ ENTRY_POINTS = {
     "dimsum_modulate": RowwiseParams,
     "dimsum_gate_residual": RowwiseParams,
     "dimsum_add_rmsnorm": RmsnormParams,
+    "dimsum_gelu_mul": GeluMulParams,
 }
 
 

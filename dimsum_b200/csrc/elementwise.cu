@@ -92,6 +92,30 @@ __global__ void __launch_bounds__(256) add_rmsnorm_kernel(const dimsum_rmsnorm_p
     }
 }
 
+// tanh-approximated GELU with an accurate tanh: tanh(y) = 1 - 2 / (exp(2y) + 1)
+DEV float gelu_tanh_f(float x) {
+    const float y = 0.7978845608028654f * fmaf(0.044715f * x * x, x, x);
+    const float t = 1.f - 2.f * rcp_mufu(1.f + ex2_mufu(2.f * kLog2e * y));
+    return 0.5f * x * (1.f + t);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) gelu_mul_kernel(const dimsum_gelu_mul_params p) {
+    constexpr int VEC = Io<T>::kVec;
+    const int vpr = (int)(p.hidden / VEC);
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= p.rows * vpr) return;
+    const int v = (int)(gid % vpr);
+    const int64_t r = gid / vpr;
+    const T *x = reinterpret_cast<const T *>(p.x) + r * p.x_row_stride;
+    float a[VEC], b[VEC], o[VEC];
+    Io<T>::ldv(x + v * VEC, a);
+    Io<T>::ldv(x + p.hidden + v * VEC, b);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) o[i] = gelu_tanh_f(a[i]) * b[i];
+    Io<T>::stv(reinterpret_cast<T *>(p.y) + r * p.y_row_stride + v * VEC, o);
+}
+
 int rowwise_entry(const dimsum_rowwise_params *p, bool gate, void *stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     const char *who = gate ? "gate_residual" : "modulate";
@@ -145,4 +169,20 @@ extern "C" int dimsum_add_rmsnorm(const dimsum_rmsnorm_params *p, void *stream_)
     else if (p->dtype == DIMSUM_BF16) add_rmsnorm_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(*p);
     else add_rmsnorm_kernel<__half><<<blocks, 256, 0, stream>>>(*p);
     return check_launch("add_rmsnorm");
+}
+
+extern "C" int dimsum_gelu_mul(const dimsum_gelu_mul_params *p, void *stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    DIMSUM_REQUIRE(p != nullptr && p->x && p->y, DIMSUM_ERR_INVALID, "gelu_mul: null pointer");
+    DIMSUM_REQUIRE(p->rows >= 0 && p->hidden > 0 && p->dtype >= 0 && p->dtype <= 2, DIMSUM_ERR_INVALID, "gelu_mul: bad arguments");
+    const int vec = p->dtype == DIMSUM_F32 ? 4 : 8;
+    DIMSUM_REQUIRE(p->hidden % vec == 0 && aligned16(p->x) && aligned16(p->y) && p->x_row_stride % vec == 0 &&
+                       p->y_row_stride % vec == 0, DIMSUM_ERR_UNSUPPORTED, "gelu_mul: rows must be 16-byte aligned");
+    if (p->rows == 0) return DIMSUM_OK;
+    const int64_t total = p->rows * (p->hidden / vec);
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    if (p->dtype == DIMSUM_F32) gelu_mul_kernel<float><<<blocks, 256, 0, stream>>>(*p);
+    else if (p->dtype == DIMSUM_BF16) gelu_mul_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(*p);
+    else gelu_mul_kernel<__half><<<blocks, 256, 0, stream>>>(*p);
+    return check_launch("gelu_mul");
 }

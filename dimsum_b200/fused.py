@@ -90,3 +90,21 @@ def add_rmsnorm(x, residual, weight, eps, want_residual=True):
         p.eps = eps
         _lib.call("dimsum_add_rmsnorm", p, torch.cuda.current_stream(x.device).cuda_stream)
     return y.view(shape), (res_out.view(shape) if res_out is not None else None)
+
+
+def gelu_mul(x12):
+    """GatedMLP activation: gelu_tanh(x12[..., :H]) * x12[..., H:] in one pass (dimsum/mlp.py:65-70)."""
+    shape = x12.shape
+    x2 = x12.reshape(-1, shape[-1])
+    if x2.stride(1) != 1:
+        x2 = x2.contiguous()
+    rows, twoH = x2.shape
+    H = twoH // 2
+    y = torch.empty((rows, H), device=x12.device, dtype=x12.dtype)
+    with torch.cuda.device(x12.device):
+        p = _lib.GeluMulParams()
+        p.rows, p.hidden, p.dtype = rows, H, _DT[x12.dtype]
+        p.x_row_stride, p.y_row_stride = x2.stride(0), y.stride(0)
+        p.x, p.y = x2.data_ptr(), y.data_ptr()
+        _lib.call("dimsum_gelu_mul", p, torch.cuda.current_stream(x12.device).cuda_stream)
+    return y.view(shape[:-1] + (H,))

@@ -17,7 +17,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import causal_conv1d_cuda, selective_scan_cuda
-from .selective_scan_interface import mamba_inner_fn
+from .selective_scan_interface import _rows_times_wt, mamba_inner_fn
 
 
 class Mamba(nn.Module):
@@ -115,13 +115,14 @@ class Mamba(nn.Module):
             x_proj_w, dt_w, out_w = x_proj_w.to(dt_), dt_w.to(dt_), out_w.to(dt_)
         conv_w = self.conv1d.weight.reshape(Dm, -1)
         u = causal_conv1d_cuda.causal_conv1d_fwd(x, conv_w, self.conv1d.bias, True, perm=order)   # permuted order
-        x_dbl = F.linear(u.transpose(1, 2).reshape(B_ * L, Dm), x_proj_w)
+        x_dbl = _rows_times_wt(u, x_proj_w).reshape(B_ * L, -1)
         delta = (dt_w @ x_dbl[:, :rank].t()).view(Dm, B_, L).transpose(0, 1)
         Bm = x_dbl[:, rank:rank + N].view(B_, L, 1, N).permute(0, 2, 3, 1).contiguous()
         Cm = x_dbl[:, rank + N:].view(B_, L, 1, N).permute(0, 2, 3, 1).contiguous()
         _, _, out_z = selective_scan_cuda.fwd(u, delta, A, Bm, Cm, self.D.float(), z, self.dt_proj.bias.float(), True,
                                               need_out=False, need_x=False, perm=order)           # natural order again
-        return F.linear(out_z.transpose(1, 2), out_w, self.out_proj.bias)
+        y = _rows_times_wt(out_z, out_w)
+        return y if self.out_proj.bias is None else y + self.out_proj.bias
 
 
 class CondMamba(Mamba):

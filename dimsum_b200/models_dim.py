@@ -146,7 +146,10 @@ class GatedMLP(nn.Module):
         self.act_layer = act_layer()
 
     def forward(self, x):
-        x1, x2 = self.w12(x).chunk(2, dim=-1)
+        x12 = self.w12(x)
+        if _fused_ok(x12) and x12.dtype in (torch.float32, torch.bfloat16, torch.float16):
+            return self.w3(fused.gelu_mul(x12))
+        x1, x2 = x12.chunk(2, dim=-1)
         return self.w3(self.act_layer(x1) * x2)
 
 

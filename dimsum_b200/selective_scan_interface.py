@@ -29,7 +29,7 @@ class SelectiveScanFn(torch.autograd.Function):
             B = B.unsqueeze(1)
         if ctx.squeeze_C:
             C = C.unsqueeze(1)
-        needs_grad = any(ctx.needs_input_grad)
+        needs_grad = torch.is_grad_enabled() and any(ctx.needs_input_grad)   # needs_input_grad ignores no_grad()
         out, x, *rest = selective_scan_cuda.fwd(u, delta, A, B, C, D, z, delta_bias, delta_softplus,
                                                 need_out=needs_grad or z is None,
                                                 need_x=needs_grad or return_last_state)
@@ -64,6 +64,13 @@ def selective_scan_fn(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_
     """if return_last_state is True, returns (out, last_state); last_state has shape (batch, dim, dstate).
     The gradient of the last state is not considered in the backward pass (as in the reference)."""
     return SelectiveScanFn.apply(u, delta, A, B, C, D, z, delta_bias, delta_softplus, return_last_state)
+
+
+def _rows_times_wt(t_bdl, weight):
+    """(B, D, L) channel-major activations x (E, D) weight -> (B, L, E), i.e. F.linear(t.transpose(1, 2), weight), as one
+    batched GEMM that consumes the transposed view in place (F.linear would first materialise a (B, L, D) copy)."""
+    w = weight.to(t_bdl.dtype) if weight.dtype != t_bdl.dtype else weight
+    return torch.bmm(t_bdl.transpose(1, 2), w.t().unsqueeze(0).expand(t_bdl.shape[0], -1, -1))
 
 
 def _autocast_weights(*ws):
@@ -102,7 +109,7 @@ class MambaInnerFn(torch.autograd.Function):
         conv_out = causal_conv1d_cuda.causal_conv1d_fwd_cond(x, conv_w, conv1d_bias, True, init_states)
         R, Dm = conv_out.shape[0], conv_out.shape[1]
         # delta keeps d slowest / l fastest, the layout the scan wants (selective_scan_interface.py:837-841)
-        x_dbl = F.linear(conv_out.transpose(1, 2).reshape(R * L, Dm), x_proj_weight)
+        x_dbl = _rows_times_wt(conv_out, x_proj_weight).reshape(R * L, -1)
         delta = (delta_proj_weight @ x_dbl[:, :rank].t()).view(Dm, R, L).transpose(0, 1)
         Bm = x_dbl[:, rank:rank + N]
         Cm = x_dbl[:, rank + N:]
@@ -113,7 +120,7 @@ class MambaInnerFn(torch.autograd.Function):
         Bm = Bm.view(R, L, 1, N).permute(0, 2, 3, 1).contiguous()
         Cm = Cm.view(R, L, 1, N).permute(0, 2, 3, 1).contiguous()
         D = D.contiguous() if D is not None else None
-        needs_grad = any(ctx.needs_input_grad)
+        needs_grad = torch.is_grad_enabled() and any(ctx.needs_input_grad)   # needs_input_grad ignores no_grad()
         out, x_ckpt, out_z = selective_scan_cuda.fwd(conv_out, delta, A, Bm, Cm, D, z, delta_bias, delta_softplus,
                                                      need_out=needs_grad, need_x=needs_grad)
         ctx.delta_softplus = delta_softplus
@@ -125,7 +132,8 @@ class MambaInnerFn(torch.autograd.Function):
                                   A, Bm, Cm, D, delta_bias, x_ckpt, out)
         if not has_out_proj:
             return out_z
-        return F.linear(out_z.transpose(1, 2), out_proj_weight, out_proj_bias)
+        y = _rows_times_wt(out_z, out_proj_weight)
+        return y if out_proj_bias is None else y + out_proj_bias
 
     @staticmethod
     @torch.amp.custom_bwd(device_type="cuda")

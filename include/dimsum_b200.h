@@ -212,6 +212,16 @@ typedef struct {
 
 int dimsum_add_rmsnorm(const dimsum_rmsnorm_params *p, void *stream);
 
+/* GatedMLP inner activation (dimsum/mlp.py:65-70): y[r, :] = gelu_tanh(x[r, :H]) * x[r, H:2H]; x (rows, 2H), y (rows, H). */
+typedef struct {
+    int64_t rows, hidden, dtype;
+    int64_t x_row_stride, y_row_stride;
+    const void *x;
+    void *y;
+} dimsum_gelu_mul_params;
+
+int dimsum_gelu_mul(const dimsum_gelu_mul_params *p, void *stream);
+
 /* ---- misc --------------------------------------------------------------------------------- */
 int dimsum_abi_version(void);
 const char *dimsum_last_error(void);

@@ -43,3 +43,13 @@ def test_add_rmsnorm_matches_oracle(dtype, C):
     assert rel_err(r, want_res) <= 1e-6
     y2, none = fused.add_rmsnorm(x.cuda(), None, w.cuda(), 1e-5, want_residual=False)
     assert none is None and rel_err(y2, ref_ops.rms_norm_oracle(x, w, eps=1e-5)) <= (2e-6 if dtype == torch.float32 else 1e-2)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_gelu_mul(dtype):
+    from dimsum_b200 import fused
+    g = torch.Generator(device="cuda").manual_seed(2)
+    x = (3 * torch.randn(7, 33, 2 * 256, generator=g, device="cuda")).to(dtype)
+    a, b = x.float().chunk(2, dim=-1)
+    want = torch.nn.functional.gelu(a, approximate="tanh") * b
+    assert rel_err(fused.gelu_mul(x), want) <= (2e-6 if dtype == torch.float32 else 1e-2)
