@@ -18,7 +18,7 @@ struct ConvArgs {
     float *dweight, *dbias;
     const int32_t *perm;
     int64_t x_bs, x_ds, o_bs, o_ds, g_bs, g_ds, dx_bs, dx_ds, w_ds, w_ws;
-    int batch, dim, seqlen, width, silu, w_dtype;
+    int batch, dim, seqlen, width, silu, w_dtype, vec_ok;
 };
 
 DEV float load_w(const void *w, int dtype, int64_t idx) {
@@ -121,7 +121,81 @@ __global__ void __launch_bounds__(kBwdThreads) conv_bwd_kernel(const ConvArgs a)
     float dw[kMaxW] = {0.f, 0.f, 0.f, 0.f};
     float db = 0.f;
 
-    // element (bl, l): g[l] = dout[l] * act'(pre[l]);  dx[l] = sum_k w[k] g[l + 3 - k];  dw[k] += g[l] x[l - 3 + k]
+    // g[l] = dout[l] * act'(pre[l]);  dx[l] = sum_j w[3-j] g[l+j];  dw[k] += g[l] x[l-3+k]
+    if (a.seqlen % Io<T>::kVec == 0 && a.vec_ok) {
+        // vector path: a thread owns one 16-byte vector; x halo comes from the lane below, g halo from the lane above
+        constexpr int VEC = Io<T>::kVec;
+        const int vpr = L / VEC;
+        const int lane = threadIdx.x & 31;
+        const int total = nb * vpr;
+        for (int base = 0; base < total; base += kBwdThreads) {
+            const int idx = base + threadIdx.x;
+            const bool act = idx < total;
+            const int bl = act ? idx / vpr : 0, v = act ? idx % vpr : 0;
+            const T *xr = reinterpret_cast<const T *>(a.x) + (b0 + bl) * a.x_bs + d * a.x_ds + v * VEC;
+            const T *gr = reinterpret_cast<const T *>(a.dout) + (b0 + bl) * a.g_bs + d * a.g_ds + v * VEC;
+            float xs[VEC + kMaxW - 1], g[VEC + kMaxW - 1];
+#pragma unroll
+            for (int i = 0; i < VEC + kMaxW - 1; ++i) { xs[i] = 0.f; g[i] = 0.f; }
+            if (act) {
+                Io<T>::ldv(xr, reinterpret_cast<float(&)[VEC]>(xs[kMaxW - 1]));
+                Io<T>::ldv(gr, reinterpret_cast<float(&)[VEC]>(g[0]));
+            }
+            const float h0 = __shfl_up_sync(0xffffffffu, xs[VEC + kMaxW - 4], 1);
+            const float h1 = __shfl_up_sync(0xffffffffu, xs[VEC + kMaxW - 3], 1);
+            const float h2 = __shfl_up_sync(0xffffffffu, xs[VEC + kMaxW - 2], 1);
+            if (act && v > 0) {
+                if (lane > 0) { xs[0] = h0; xs[1] = h1; xs[2] = h2; }
+                else { xs[0] = Io<T>::ld(xr - 3); xs[1] = Io<T>::ld(xr - 2); xs[2] = Io<T>::ld(xr - 1); }
+            }
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                if (a.silu) {
+                    float pre = bias;
+#pragma unroll
+                    for (int k = 0; k < kMaxW; ++k) pre = fmaf(w[k], xs[i + k], pre);
+                    const float sg = sigmoid_f(pre);
+                    g[i] *= sg * fmaf(pre, 1.f - sg, 1.f);
+                }
+                db += g[i];
+#pragma unroll
+                for (int k = 0; k < kMaxW; ++k) dw[k] = fmaf(g[i], xs[i + k], dw[k]);
+            }
+            // first 3 g's of the next vector of the same row
+            const float n0 = __shfl_down_sync(0xffffffffu, g[0], 1);
+            const float n1 = __shfl_down_sync(0xffffffffu, g[1], 1);
+            const float n2 = __shfl_down_sync(0xffffffffu, g[2], 1);
+            if (act && v + 1 < vpr) {
+                if (lane < 31 && idx + 1 < total) {
+                    g[VEC] = n0; g[VEC + 1] = n1; g[VEC + 2] = n2;
+                } else {   // warp edge: recompute the neighbour's first three g's
+#pragma unroll
+                    for (int j = 0; j < kMaxW - 1; ++j) {
+                        float gg = Io<T>::ld(gr + VEC + j);
+                        if (a.silu) {
+                            float pre = bias;
+#pragma unroll
+                            for (int k = 0; k < kMaxW; ++k) pre = fmaf(w[k], Io<T>::ld(xr + VEC + j - (kMaxW - 1) + k), pre);
+                            const float sg = sigmoid_f(pre);
+                            gg *= sg * fmaf(pre, 1.f - sg, 1.f);
+                        }
+                        g[VEC + j] = gg;
+                    }
+                }
+            }
+            if (act) {
+                float dxv[VEC];
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int j = 0; j < kMaxW; ++j) acc = fmaf(w[kMaxW - 1 - j], g[i + j], acc);
+                    dxv[i] = acc;
+                }
+                Io<T>::stv(reinterpret_cast<T *>(a.dx) + (b0 + bl) * a.dx_bs + d * a.dx_ds + v * VEC, dxv);
+            }
+        }
+    } else
     for (int64_t idx = threadIdx.x; idx < (int64_t)nb * L; idx += kBwdThreads) {
         const int bl = (int)(idx / L), l = (int)(idx % L);
         const T *xr = reinterpret_cast<const T *>(a.x) + (b0 + bl) * a.x_bs + d * a.x_ds;
@@ -250,6 +324,11 @@ extern "C" int dimsum_causal_conv1d_bwd(const dimsum_conv_bwd_params *p, void *s
     a.dx_bs = p->dx_batch_stride; a.dx_ds = p->dx_d_stride; a.w_ds = p->w_d_stride; a.w_ws = p->w_width_stride;
     a.batch = (int)p->batch; a.dim = (int)p->dim; a.seqlen = (int)p->seqlen; a.width = (int)p->width;
     a.silu = p->silu != 0; a.w_dtype = (int)p->w_dtype;
+    {
+        const int vec = p->io_dtype == DIMSUM_F32 ? 4 : 8;
+        a.vec_ok = aligned16(p->x) && aligned16(p->dout) && aligned16(p->dx) && a.x_bs % vec == 0 && a.x_ds % vec == 0 &&
+                   a.g_bs % vec == 0 && a.g_ds % vec == 0 && a.dx_bs % vec == 0 && a.dx_ds % vec == 0;
+    }
     switch (p->io_dtype) {
         case DIMSUM_F32: return run_bwd<float>(a, stream);
         case DIMSUM_BF16: return run_bwd<__nv_bfloat16>(a, stream);

@@ -47,7 +47,7 @@ struct BwdSmem {
     float du[kRowsB][kPitch];
     float Bs[kSub][kPitch];
     float Cs[kSub][kPitch];
-    float part[kThreadsB / 32][kSub][32];   // per-warp dB/dC partial sums: [l][0..15] = dB_n, [l][16..31] = dC_n
+    float part[kThreadsB / 32][kSub][33];   // per-warp dB/dC partial sums: [l][0..15] = dB_n, [l][16..31] = dC_n (+1 pad)
 };
 
 template <typename T, bool kHasZ>

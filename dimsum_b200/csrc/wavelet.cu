@@ -54,9 +54,38 @@ DEV int patch_pixel(int j2, int j1) {
 
 constexpr int kWaveThreads = 256;
 
-template <typename T, bool kInverse>
+// 4 consecutive channels: one 16-byte (fp32) or 8-byte (16-bit) access
+template <typename T> DEV void ld4(const T *p, float (&v)[4]);
+template <typename T> DEV void st4(T *p, const float (&v)[4]);
+template <> DEV void ld4<float>(const float *p, float (&v)[4]) {
+    const float4 r = *reinterpret_cast<const float4 *>(p);
+    v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w;
+}
+template <> DEV void st4<float>(float *p, const float (&v)[4]) { *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+template <> DEV void ld4<__nv_bfloat16>(const __nv_bfloat16 *p, float (&v)[4]) {
+    const uint2 r = *reinterpret_cast<const uint2 *>(p);
+    v[0] = __uint_as_float(r.x << 16); v[1] = __uint_as_float(r.x & 0xffff0000u);
+    v[2] = __uint_as_float(r.y << 16); v[3] = __uint_as_float(r.y & 0xffff0000u);
+}
+template <> DEV void st4<__nv_bfloat16>(__nv_bfloat16 *p, const float (&v)[4]) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+    *reinterpret_cast<uint2 *>(p) = make_uint2(reinterpret_cast<uint32_t &>(a), reinterpret_cast<uint32_t &>(b));
+}
+template <> DEV void ld4<__half>(const __half *p, float (&v)[4]) {
+    const uint2 r = *reinterpret_cast<const uint2 *>(p);
+    const float2 a = __half22float2(reinterpret_cast<const __half2 &>(r.x)), b = __half22float2(reinterpret_cast<const __half2 &>(r.y));
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+template <> DEV void st4<__half>(__half *p, const float (&v)[4]) {
+    __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
+    *reinterpret_cast<uint2 *>(p) = make_uint2(reinterpret_cast<uint32_t &>(a), reinterpret_cast<uint32_t &>(b));
+}
+
+// kVec4: every thread moves 4 consecutive channels per access (needs 16-byte aligned fp32 rows / 8-byte aligned 16-bit rows)
+template <typename T, bool kInverse, bool kVec4>
 __global__ void __launch_bounds__(kWaveThreads) wavelet_kernel(const WaveArgs a) {
-    extern __shared__ __align__(16) float tile[];   // [16][C + 4]
+    extern __shared__ __align__(16) float tile[];   // [16][C + 4] fp32
+    constexpr int CH = kVec4 ? 4 : 1;
     const int C = a.channels, pitch = C + 4, Cq = C / 16;
     const int g = a.grid / 4;
     const int b = blockIdx.y;
@@ -65,53 +94,77 @@ __global__ void __launch_bounds__(kWaveThreads) wavelet_kernel(const WaveArgs a)
     T *dst = reinterpret_cast<T *>(a.dst) + b * a.d_bs;
 
     auto token_of = [&](int t16) { return (ph * 4 + (t16 >> 2)) * a.grid + pw * 4 + (t16 & 3); };
+    auto seq_of = [&](int t16) { const int tok = token_of(t16); return a.pos != nullptr ? a.pos[tok] : tok; };
+    auto ldc = [&](const T *p, float (&v)[CH]) {
+        if constexpr (kVec4) ld4<T>(p, v); else v[0] = Io<T>::ld(p);
+    };
+    auto stc = [&](T *p, const float (&v)[CH]) {
+        if constexpr (kVec4) st4<T>(p, v); else Io<T>::st(p, v[0]);
+    };
 
     if (!kInverse) {
         // image tokens -> butterfly -> tile[p1p2][k * Cq + c / 16] -> coefficient tokens at pos[token]
-        for (int c = threadIdx.x; c < C; c += kWaveThreads) {
-            float v[16];
+        for (int c0 = threadIdx.x * CH; c0 < C; c0 += kWaveThreads * CH) {
+            float px[16][CH];
 #pragma unroll
             for (int j2 = 0; j2 < 4; ++j2)
 #pragma unroll
                 for (int j1 = 0; j1 < 4; ++j1)
-                    v[4 * j2 + j1] = Io<T>::ld(src + (int64_t)token_of(patch_pixel(j2, j1)) * a.s_ts + c);
-            packet16(v);
-            const int t16 = c & 15, cq = c >> 4;
+                    ldc(src + (int64_t)token_of(patch_pixel(j2, j1)) * a.s_ts + c0, px[4 * j2 + j1]);
 #pragma unroll
-            for (int k = 0; k < 16; ++k) tile[t16 * pitch + k * Cq + cq] = v[k] * a.scale;
+            for (int i = 0; i < CH; ++i) {
+                float v[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) v[k] = px[k][i];
+                packet16(v);
+                const int c = c0 + i, t16 = c & 15, cq = c >> 4;
+#pragma unroll
+                for (int k = 0; k < 16; ++k) tile[t16 * pitch + k * Cq + cq] = v[k] * a.scale;
+            }
         }
         __syncthreads();
-        for (int idx = threadIdx.x; idx < 16 * C; idx += kWaveThreads) {
+        for (int idx = threadIdx.x * CH; idx < 16 * C; idx += kWaveThreads * CH) {
             const int t16 = idx / C, c = idx % C;
-            const int tok = token_of(t16);
-            const int seq = a.pos != nullptr ? a.pos[tok] : tok;
-            Io<T>::st(dst + (int64_t)seq * a.d_ts + c, tile[t16 * pitch + c]);
+            float v[CH];
+            if constexpr (kVec4) {
+                const float4 r = *reinterpret_cast<const float4 *>(&tile[t16 * pitch + c]);
+                v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w;
+            } else {
+                v[0] = tile[t16 * pitch + c];
+            }
+            stc(dst + (int64_t)seq_of(t16) * a.d_ts + c, v);
         }
     } else {
-        for (int idx = threadIdx.x; idx < 16 * C; idx += kWaveThreads) {
+        for (int idx = threadIdx.x * CH; idx < 16 * C; idx += kWaveThreads * CH) {
             const int t16 = idx / C, c = idx % C;
-            const int tok = token_of(t16);
-            const int seq = a.pos != nullptr ? a.pos[tok] : tok;
-            tile[t16 * pitch + c] = Io<T>::ld(src + (int64_t)seq * a.s_ts + c);
+            float v[CH];
+            ldc(src + (int64_t)seq_of(t16) * a.s_ts + c, v);
+            if constexpr (kVec4) {
+                *reinterpret_cast<float4 *>(&tile[t16 * pitch + c]) = make_float4(v[0], v[1], v[2], v[3]);
+            } else {
+                tile[t16 * pitch + c] = v[0];
+            }
         }
         __syncthreads();
-        for (int c = threadIdx.x; c < C; c += kWaveThreads) {
-            float v[16];
-            const int t16 = c & 15, cq = c >> 4;
+        for (int c0 = threadIdx.x * CH; c0 < C; c0 += kWaveThreads * CH) {
+            float px[16][CH];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) v[k] = tile[t16 * pitch + k * Cq + cq];
-            // inverse = the same sign butterfly with the roles of (k1,k2) and (j1,j2) exchanged
-            float tmp[16];
+            for (int i = 0; i < CH; ++i) {
+                const int c = c0 + i, t16 = c & 15, cq = c >> 4;
+                // inverse = the same sign butterfly with the roles of (k1,k2) and (j1,j2) exchanged
+                float tmp[16];
 #pragma unroll
-            for (int k1 = 0; k1 < 4; ++k1)
+                for (int k1 = 0; k1 < 4; ++k1)
 #pragma unroll
-                for (int k2 = 0; k2 < 4; ++k2) tmp[4 * k2 + k1] = v[4 * k1 + k2];   // -> [k2][k1] so packet16 maps k1->j1 first
-            packet16(tmp);   // tmp[4*j1 + j2]
+                    for (int k2 = 0; k2 < 4; ++k2) tmp[4 * k2 + k1] = tile[t16 * pitch + (4 * k1 + k2) * Cq + cq];
+                packet16(tmp);   // tmp[4*j1 + j2]
 #pragma unroll
-            for (int j1 = 0; j1 < 4; ++j1)
+                for (int j1 = 0; j1 < 4; ++j1)
 #pragma unroll
-                for (int j2 = 0; j2 < 4; ++j2)
-                    Io<T>::st(dst + (int64_t)token_of(patch_pixel(j2, j1)) * a.d_ts + c, tmp[4 * j1 + j2] * a.scale);
+                    for (int j2 = 0; j2 < 4; ++j2) px[patch_pixel(j2, j1)][i] = tmp[4 * j1 + j2] * a.scale;
+            }
+#pragma unroll
+            for (int t = 0; t < 16; ++t) stc(dst + (int64_t)token_of(t) * a.d_ts + c0, px[t]);
         }
     }
 }
@@ -138,14 +191,17 @@ int run_wavelet(const dimsum_wavelet_params *p, bool inverse, cudaStream_t strea
     const int g = a.grid / 4;
     const int smem = 16 * (a.channels + 4) * (int)sizeof(float);
     dim3 grid(g * g, (unsigned)p->batch);
+    const uintptr_t align = 4 * sizeof(T) - 1;
+    const bool vec4 = ((reinterpret_cast<uintptr_t>(p->src) | reinterpret_cast<uintptr_t>(p->dst)) & align) == 0 &&
+                      a.s_bs % 4 == 0 && a.s_ts % 4 == 0 && a.d_bs % 4 == 0 && a.d_ts % 4 == 0;
+    auto go = [&](auto kern) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        kern<<<grid, kWaveThreads, smem, stream>>>(a);
+    };
     if (inverse) {
-        auto k = wavelet_kernel<T, true>;
-        if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        k<<<grid, kWaveThreads, smem, stream>>>(a);
+        if (vec4) go(wavelet_kernel<T, true, true>); else go(wavelet_kernel<T, true, false>);
     } else {
-        auto k = wavelet_kernel<T, false>;
-        if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        k<<<grid, kWaveThreads, smem, stream>>>(a);
+        if (vec4) go(wavelet_kernel<T, false, true>); else go(wavelet_kernel<T, false, false>);
     }
     return check_launch(inverse ? "wavelet_packet_inv" : "wavelet_packet_fwd");
 }

@@ -20,7 +20,8 @@ class SelectiveScanFn(torch.autograd.Function):
     """selective_scan_interface.py:12-91."""
 
     @staticmethod
-    def forward(ctx, u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False, return_last_state=False):
+    def forward(ctx, u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False, return_last_state=False,
+                recording=True):
         u, delta, B, C, z = map(_last_contig, (u, delta, B, C, z))
         D = D.contiguous() if D is not None else None
         ctx.squeeze_B = B.dim() == 3
@@ -29,7 +30,9 @@ class SelectiveScanFn(torch.autograd.Function):
             B = B.unsqueeze(1)
         if ctx.squeeze_C:
             C = C.unsqueeze(1)
-        needs_grad = torch.is_grad_enabled() and any(ctx.needs_input_grad)   # needs_input_grad ignores no_grad()
+        # `recording` is torch.is_grad_enabled() sampled by the caller: inside forward() grad mode is always off, and
+        # ctx.needs_input_grad ignores no_grad()
+        needs_grad = recording and any(ctx.needs_input_grad)
         out, x, *rest = selective_scan_cuda.fwd(u, delta, A, B, C, D, z, delta_bias, delta_softplus,
                                                 need_out=needs_grad or z is None,
                                                 need_x=needs_grad or return_last_state)
@@ -57,13 +60,14 @@ class SelectiveScanFn(torch.autograd.Function):
         dB = dB.squeeze(1) if ctx.squeeze_B else dB
         dC = dC.squeeze(1) if ctx.squeeze_C else dC
         return (du, ddelta, dA, dB, dC, dD if D is not None else None, dz,
-                ddelta_bias if delta_bias is not None else None, None, None)
+                ddelta_bias if delta_bias is not None else None, None, None, None)
 
 
 def selective_scan_fn(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False, return_last_state=False):
     """if return_last_state is True, returns (out, last_state); last_state has shape (batch, dim, dstate).
     The gradient of the last state is not considered in the backward pass (as in the reference)."""
-    return SelectiveScanFn.apply(u, delta, A, B, C, D, z, delta_bias, delta_softplus, return_last_state)
+    return SelectiveScanFn.apply(u, delta, A, B, C, D, z, delta_bias, delta_softplus, return_last_state,
+                                 torch.is_grad_enabled())
 
 
 def _rows_times_wt(t_bdl, weight):
@@ -92,7 +96,7 @@ class MambaInnerFn(torch.autograd.Function):
     @torch.amp.custom_fwd(device_type="cuda")
     def forward(ctx, xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, out_proj_weight, out_proj_bias,
                 A, B=None, C=None, D=None, delta_bias=None, B_proj_bias=None, C_proj_bias=None, delta_softplus=True,
-                init_states=None, has_out_proj=True):
+                init_states=None, has_out_proj=True, recording=True):
         if B is not None or C is not None:
             raise NotImplementedError("mamba_inner_fn: only input-dependent B and C are implemented")
         if A.is_complex():
@@ -120,7 +124,7 @@ class MambaInnerFn(torch.autograd.Function):
         Bm = Bm.view(R, L, 1, N).permute(0, 2, 3, 1).contiguous()
         Cm = Cm.view(R, L, 1, N).permute(0, 2, 3, 1).contiguous()
         D = D.contiguous() if D is not None else None
-        needs_grad = torch.is_grad_enabled() and any(ctx.needs_input_grad)   # needs_input_grad ignores no_grad()
+        needs_grad = recording and any(ctx.needs_input_grad)
         out, x_ckpt, out_z = selective_scan_cuda.fwd(conv_out, delta, A, Bm, Cm, D, z, delta_bias, delta_softplus,
                                                      need_out=needs_grad, need_x=needs_grad)
         ctx.delta_softplus = delta_softplus
@@ -178,13 +182,13 @@ class MambaInnerFn(torch.autograd.Function):
         dx, dconv_w, dconv_b = causal_conv1d_cuda.causal_conv1d_bwd(x, conv_w, conv1d_bias, dconv_out, dx, True)
         return (dxz, dconv_w.unsqueeze(1), dconv_b if conv1d_bias is not None else None, dx_proj_weight,
                 ddelta_proj_weight, dout_proj_weight, dout_proj_bias, dA, None, None, dD,
-                ddelta_bias if delta_bias is not None else None, dB_proj_bias, dC_proj_bias, None, None, None)
+                ddelta_bias if delta_bias is not None else None, dB_proj_bias, dC_proj_bias, None, None, None, None)
 
 
 def mamba_inner_fn(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, out_proj_weight, out_proj_bias,
                    A, B=None, C=None, D=None, delta_bias=None, B_proj_bias=None, C_proj_bias=None, delta_softplus=True):
     return MambaInnerFn.apply(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, out_proj_weight,
-                              out_proj_bias, A, B, C, D, delta_bias, B_proj_bias, C_proj_bias, delta_softplus, None, True)
+                              out_proj_bias, A, B, C, D, delta_bias, B_proj_bias, C_proj_bias, delta_softplus, None, True, torch.is_grad_enabled())
 
 
 def mamba_inner_fn_cond(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, out_proj_weight,
@@ -192,17 +196,17 @@ def mamba_inner_fn_cond(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_pro
                         delta_softplus=True, init_states=None):
     return MambaInnerFn.apply(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, out_proj_weight,
                               out_proj_bias, A, B, C, D, delta_bias, B_proj_bias, C_proj_bias, delta_softplus,
-                              init_states, True)
+                              init_states, True, torch.is_grad_enabled())
 
 
 def mamba_inner_fn_no_out_proj(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, A, B=None, C=None,
                                D=None, delta_bias=None, B_proj_bias=None, C_proj_bias=None, delta_softplus=True):
     return MambaInnerFn.apply(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, None, None, A, B, C, D,
-                              delta_bias, B_proj_bias, C_proj_bias, delta_softplus, None, False)
+                              delta_bias, B_proj_bias, C_proj_bias, delta_softplus, None, False, torch.is_grad_enabled())
 
 
 def mamba_inner_fn_no_out_proj_cond(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, A, B=None, C=None,
                                     D=None, delta_bias=None, B_proj_bias=None, C_proj_bias=None, delta_softplus=True,
                                     init_states=None):
     return MambaInnerFn.apply(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, None, None, A, B, C, D,
-                              delta_bias, B_proj_bias, C_proj_bias, delta_softplus, init_states, False)
+                              delta_bias, B_proj_bias, C_proj_bias, delta_softplus, init_states, False, torch.is_grad_enabled())
