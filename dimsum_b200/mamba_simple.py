@@ -41,6 +41,10 @@ class Mamba(nn.Module):
         if d_cond is not None:
             # kept for checkpoint compatibility; its output never influences the result
             self.cond_proj = nn.Linear(d_cond, self.d_inner, bias=True, **fk)
+            # the reference returns dcond=None (selective_scan_interface.py:935,1006), so these never receive a gradient;
+            # frozen here so that DDP (find_unused_parameters=False, train.py:180) does not wait for them
+            for prm in self.cond_proj.parameters():
+                prm.requires_grad_(False)
         # dt_proj keeps the variance of delta at init; its bias is softplus^-1 of a log-uniform step in [dt_min, dt_max]
         std = self.dt_rank ** -0.5 * dt_scale
         if dt_init == "constant":

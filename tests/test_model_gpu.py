@@ -64,3 +64,28 @@ def test_scan_table_orders_match_explicit_gathers():
         got = mixer(h)
         want = plain(h[:, fwd[5].cuda()])[:, rev[5].cuda()]
     assert rel_err(got, want) <= 1e-5
+
+
+def test_fixed_seed_cfg_sampling_matches_oracle_sampler():
+    """Fixed-seed CFG Euler sampling (sample_ddp.py:159-178 with the fixed-grid euler of integrators.py:98-111): the final
+    latent of the GPU path matches the CPU oracle sampler run from the same noise, labels and weights."""
+    from dimsum_b200.models_dim import DiM
+    from dimsum_b200.sampler import sample_cfg
+    from oracle import ref_model
+    raw, sd = _load("toy256")
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        m = DiM(img_resolution=32, in_channels=4, hidden_size=64, depth=5, num_classes=10, label_dropout=0.1)
+        m.load_state_dict(sd, strict=True)
+        m = m.cuda().eval()
+        g = torch.Generator().manual_seed(123)
+        z = torch.randn(2, 4, 32, 32, generator=g)
+        y = torch.randint(0, 10, (2,), generator=g)
+        steps = 40
+        got = sample_cfg(m, z.cuda(), y.cuda(), cfg_scale=4.0, num_steps=steps)
+        with torch.no_grad():
+            want = ref_model.euler_sample_oracle(sd, z, y, 4.0, num_steps=steps, null_class=10)
+        assert rel_err(got, want) <= 1e-4, rel_err(got, want)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
