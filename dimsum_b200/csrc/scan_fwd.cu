@@ -54,13 +54,30 @@ DEV void cp_async16(void *smem, const void *gmem) {
 DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::); }
 DEV void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// x[b][d][chunk32][2n + slot]: slot 0 = h after 16 steps of the 32-step chunk, slot 1 = h after the chunk.
-DEV void store_state(const ScanFwdArgs &a, int b, int d, int chunk, int slot, const float2 (&h2)[kNS / 2]) {
-    float *xp = a.x + (((int64_t)b * a.dim + d) * a.n_chunks + chunk) * (2 * a.dstate) + slot;
+// Checkpoints for the backward: record c of x[b][d][c][0 .. 2N) holds, PLANAR, h after step 32c+16 in [0, N) and h after
+// step 32c+32 in [N, 2N) -- 64 contiguous bytes per store, i.e. full sectors.  (half = 0 / 1.)
+DEV void store_state(const ScanFwdArgs &a, int b, int d, int chunk, int half, const float2 (&h2)[kNS / 2]) {
+    float *xp = a.x + (((int64_t)b * a.dim + d) * a.n_chunks + chunk) * (2 * a.dstate) + half * a.dstate;
+    if (a.dstate == kNS) {
+#pragma unroll
+        for (int p = 0; p < kNS / 2; p += 2)
+            *reinterpret_cast<float4 *>(xp + 2 * p) = make_float4(h2[p].x, h2[p].y, h2[p + 1].x, h2[p + 1].y);
+    } else {
+#pragma unroll
+        for (int p = 0; p < kNS / 2; ++p) {
+            if (2 * p < a.dstate) xp[2 * p] = h2[p].x;
+            if (2 * p + 1 < a.dstate) xp[2 * p + 1] = h2[p].y;
+        }
+    }
+}
+// The last record (index n_chunks - 1) keeps the reference's interleaved convention so that
+// last_state = x[:, :, -1, 1::2] (selective_scan_interface.py:39) still reads the final state.
+DEV void store_last_state(const ScanFwdArgs &a, int b, int d, const float2 (&h2)[kNS / 2]) {
+    float *xp = a.x + (((int64_t)b * a.dim + d) * a.n_chunks + (a.n_chunks - 1)) * (2 * a.dstate);
 #pragma unroll
     for (int p = 0; p < kNS / 2; ++p) {
-        if (2 * p < a.dstate) xp[4 * p] = h2[p].x;
-        if (2 * p + 1 < a.dstate) xp[4 * p + 2] = h2[p].y;
+        if (2 * p < a.dstate) { xp[4 * p] = 0.f; xp[4 * p + 1] = h2[p].x; }
+        if (2 * p + 1 < a.dstate) { xp[4 * p + 2] = 0.f; xp[4 * p + 3] = h2[p].y; }
     }
 }
 
@@ -286,8 +303,7 @@ __global__ void __launch_bounds__(kRows, 3) scan_fwd_kernel(const ScanFwdArgs a)
             }
         }
     }
-    // final state in slot 1 of the last 32-chunk even when L is not a multiple of 32
-    if (a.x != nullptr && row_ok) store_state(a, b, d0 + tid, (L - 1) / 32, 1, h2);
+    if (a.x != nullptr && row_ok) store_last_state(a, b, d0 + tid, h2);
 }
 
 template <typename T, bool kHasZ, bool kSoftplus, int kPoly, int kPolyDeg>
@@ -359,8 +375,8 @@ extern "C" int dimsum_selective_scan_fwd(const dimsum_scan_fwd_params *p, void *
                    (long long)p->io_dtype);
     if (p->x != nullptr) {
         DIMSUM_REQUIRE(p->chunk_len == 32, DIMSUM_ERR_INVALID, "selective_scan_fwd: chunk_len must be 32");
-        DIMSUM_REQUIRE(p->n_chunks == (p->seqlen + 31) / 32, DIMSUM_ERR_INVALID,
-                       "selective_scan_fwd: n_chunks must be ceil(seqlen / 32)");
+        DIMSUM_REQUIRE(p->n_chunks == (p->seqlen + 31) / 32 + 1, DIMSUM_ERR_INVALID,
+                       "selective_scan_fwd: n_chunks must be ceil(seqlen / 32) + 1");
     }
     DIMSUM_REQUIRE(p->batch <= 65535, DIMSUM_ERR_UNSUPPORTED, "selective_scan_fwd: batch > 65535");
     if (p->batch == 0) return DIMSUM_OK;

@@ -5,9 +5,10 @@
 (include/dimsum_b200.h) as raw pointers + element strides on the caller's current CUDA stream.
 
 Differences, all deliberate and visible:
-  * the layout of `x` (scan_intermediates) is private to this library: (batch, dim, ceil(L/32), 2*dstate) with
-    [..., 1::2] = state after the chunk (so the reference's `last_state = x[:, :, -1, 1::2]` still holds) and
-    [..., 0::2] = state in the middle of the chunk -- the backward's 16-step checkpoints;
+  * the layout of `x` (scan_intermediates) is private to this library: (batch, dim, ceil(L/32) + 1, 2*dstate).  Record c
+    holds, planar, the state after step 32c+16 in [:dstate] and after step 32c+32 in [dstate:] -- the backward's
+    16-step checkpoints -- and the last record keeps the reference's interleaved convention, so
+    `last_state = x[:, :, -1, 1::2]` (selective_scan_interface.py:39) still holds;
   * complex A, constant (2-D) B/C and dstate > 16 raise NotImplementedError instead of running (no fallback).
 """
 import torch
@@ -69,7 +70,7 @@ def fwd(u, delta, A, B, C, D_, z_, delta_bias_, delta_softplus, *, need_out=True
     has_z = z_ is not None
     _check(need_out or has_z, "selective_scan: nothing to compute (no out, no z)")
     with torch.cuda.device(u.device):
-        n_chunks = (seqlen + CHUNK - 1) // CHUNK
+        n_chunks = (seqlen + CHUNK - 1) // CHUNK + 1
         # reference: out = empty_like(delta) (inherits delta's layout), out_z = empty_like(z) (selective_scan.cpp:304,311)
         out = torch.empty_like(delta) if need_out else None
         out_z = torch.empty_like(z_) if has_z else None
@@ -108,7 +109,7 @@ def bwd(u, delta, A, B, C, D_, z_, delta_bias_, dout, x_, out_, dz_, delta_softp
     _check(dout.dtype == u.dtype and dout.is_cuda and dout.stride(-1) == 1 and tuple(dout.shape) == (batch, dim, seqlen),
            "selective_scan_bwd: dout must match u in dtype and shape with stride(-1) == 1")
     has_z = z_ is not None
-    n_chunks = (seqlen + CHUNK - 1) // CHUNK
+    n_chunks = (seqlen + CHUNK - 1) // CHUNK + 1
     _check(x_ is not None, "selective_scan_bwd: the forward's scan_intermediates (x) are required")
     _check(x_.dtype == torch.float32 and x_.is_cuda and x_.is_contiguous()
            and tuple(x_.shape) == (batch, dim, n_chunks, 2 * dstate), "selective_scan_bwd: x has the wrong shape")

@@ -50,13 +50,14 @@ typedef enum { DIMSUM_F32 = 0, DIMSUM_F16 = 1, DIMSUM_BF16 = 2 } dimsum_dtype;
  * A                       : (dim, dstate) fp32
  * B, C                    : (batch, n_groups, dstate, seqlen) io_dtype ("variable" B and C)
  * D, delta_bias           : (dim) fp32 or NULL
- * x                       : (batch, dim, n_chunks, 2*dstate) fp32 contiguous or NULL, chunk_len = 32,
- *                           n_chunks = ceil(seqlen/32).  x[..., 2n+1] = state h_n after the chunk (so the
- *                           reference's last_state = x[:, :, -1, 1::2] holds, selective_scan_interface.py:39),
- *                           x[..., 2n] = h_n after the first 16 steps of the chunk: together the 16-step
- *                           checkpoints the backward restarts from.  (The reference stores (prod a, h) per
- *                           2048-step chunk, selective_scan_fwd_kernel.cuh:251-254; only its own backward
- *                           kernel, replaced here, ever reads the even slots.)
+ * x                       : (batch, dim, n_chunks, 2*dstate) fp32 contiguous or NULL; chunk_len = 32 and
+ *                           n_chunks = ceil(seqlen/32) + 1.  Record c < n_chunks-1 holds, planar, the state h after
+ *                           step 32c+16 in [0, dstate) and after step 32c+32 in [dstate, 2*dstate): the 16-step
+ *                           checkpoints the backward restarts from.  The LAST record keeps the reference's
+ *                           interleaved convention (odd slots = final state), so the reference's
+ *                           last_state = x[:, :, -1, 1::2] (selective_scan_interface.py:39) holds.  (The reference
+ *                           stores (prod a, h) per 2048-step chunk, selective_scan_fwd_kernel.cuh:251-254; only its
+ *                           own backward kernel, replaced here, reads those.)
  * out                     : pre-gate y (needed by backward) or NULL (inference)
  * z / out_z               : both NULL or both set; out_z = y * silu(z)
  * perm                    : NULL, or int32[seqlen]: z is read at, and out_z written to, token perm[l]
