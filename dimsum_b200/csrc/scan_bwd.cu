@@ -52,7 +52,7 @@ struct BwdSmem {
     float Bs[kSub][kPitch];
     float Cs[kSub][kPitch];
     float ck[kRowsB][kCkPitch];              // state at the start of each mini-chunk
-    float red[kThreadsB / 32][16][kRedPitch];   // per-warp dB/dC reduction tile
+    float red[kThreadsB / 32][2][16][kRedPitch];   // per-warp dB/dC reduction tile, double-buffered by step parity
     float acc[kSub][32 + 1];                 // CTA sums for the chunk: [l][0..15] = dB_n, [l][16..31] = dC_n
 };
 
@@ -291,9 +291,10 @@ __global__ void __launch_bounds__(kThreadsB, 3) scan_bwd_kernel(const ScanBwdArg
                 } else {
                     s.du[row][li] = fmaf(dlt, G, Dv * dyv);
                 }
-                // dB / dC of the warp's 16 rows: private tile, column sums, two shuffle rounds, CTA accumulator
-                __syncwarp();
-                float *rp = &s.red[warp][rw][n0];
+                // dB / dC of the warp's 16 rows: private tile (double-buffered by step parity, so one __syncwarp per step
+                // and the read-back latency overlaps the next step's arithmetic), column sums, two shuffle rounds, CTA sums
+                float(*red)[kRedPitch] = s.red[warp][li & 1];
+                float *rp = &red[rw][n0];
                 *reinterpret_cast<float4 *>(rp) = make_float4(dBp[0].x, dBp[0].y, dBp[1].x, dBp[1].y);
                 *reinterpret_cast<float4 *>(rp + 4) = make_float4(dBp[2].x, dBp[2].y, dBp[3].x, dBp[3].y);
                 *reinterpret_cast<float4 *>(rp + 16) = make_float4(dCp[0].x, dCp[0].y, dCp[1].x, dCp[1].y);
@@ -301,12 +302,12 @@ __global__ void __launch_bounds__(kThreadsB, 3) scan_bwd_kernel(const ScanBwdArg
                 __syncwarp();
                 {
                     const int rg = lane >> 3, cg = lane & 7;                 // rows 4 rg .. 4 rg + 3, columns 4 cg .. 4 cg + 3
-                    float4 v = *reinterpret_cast<const float4 *>(&s.red[warp][4 * rg][4 * cg]);
-#pragma unroll
-                    for (int r = 1; r < 4; ++r) {
-                        const float4 w = *reinterpret_cast<const float4 *>(&s.red[warp][4 * rg + r][4 * cg]);
-                        v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
-                    }
+                    const float4 w0 = *reinterpret_cast<const float4 *>(&red[4 * rg][4 * cg]);
+                    const float4 w1 = *reinterpret_cast<const float4 *>(&red[4 * rg + 1][4 * cg]);
+                    const float4 w2 = *reinterpret_cast<const float4 *>(&red[4 * rg + 2][4 * cg]);
+                    const float4 w3 = *reinterpret_cast<const float4 *>(&red[4 * rg + 3][4 * cg]);
+                    float4 v = make_float4((w0.x + w1.x) + (w2.x + w3.x), (w0.y + w1.y) + (w2.y + w3.y),
+                                           (w0.z + w1.z) + (w2.z + w3.z), (w0.w + w1.w) + (w2.w + w3.w));
 #pragma unroll
                     for (int o = 8; o <= 16; o <<= 1) {
                         v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
