@@ -28,35 +28,41 @@ DEV float load_w(const void *w, int dtype, int64_t idx) {
 }
 
 // ---------------------------------------------------------------------------------------------- forward
-template <typename T>
+// kNV consecutive 16-byte vectors per thread (2 when the row length allows it: twice the bytes in flight per thread,
+// which is what a pure streaming kernel at full occupancy needs to cover HBM latency on B200).
+template <typename T, int kNV>
 __global__ void __launch_bounds__(256) conv_fwd_vec_kernel(const ConvArgs a) {
     constexpr int VEC = Io<T>::kVec;
-    const int vpr = a.seqlen / VEC;
+    constexpr int W = kNV * VEC;                      // elements per thread
+    const int tpr = a.seqlen / W;                     // threads per row
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t total = (int64_t)a.batch * a.dim * vpr;
+    const int64_t total = (int64_t)a.batch * a.dim * tpr;
     const bool active = gid < total;
     const int lane = threadIdx.x & 31;
-    const int v = active ? (int)(gid % vpr) : 0;
-    const int64_t row = active ? gid / vpr : 0;
+    const int v = active ? (int)(gid % tpr) : 0;
+    const int64_t row = active ? gid / tpr : 0;
     const int d = (int)(row % a.dim);
     const int b = (int)(row / a.dim);
-    const T *xr = reinterpret_cast<const T *>(a.x) + b * a.x_bs + d * a.x_ds;
+    const T *xr = reinterpret_cast<const T *>(a.x) + b * a.x_bs + d * a.x_ds + v * W;
 
-    float xv[VEC + kMaxW - 1];   // [0..2] halo, [3..] own vector
+    float xv[W + kMaxW - 1];   // [0..2] halo, [3..] own elements
 #pragma unroll
-    for (int i = 0; i < VEC + kMaxW - 1; ++i) xv[i] = 0.f;
-    if (active) Io<T>::ldv(xr + v * VEC, reinterpret_cast<float(&)[VEC]>(xv[kMaxW - 1]));
-    // halo: last 3 elements of the previous vector of the same row
-    float h0 = __shfl_up_sync(0xffffffffu, xv[VEC + kMaxW - 4], 1);
-    float h1 = __shfl_up_sync(0xffffffffu, xv[VEC + kMaxW - 3], 1);
-    float h2 = __shfl_up_sync(0xffffffffu, xv[VEC + kMaxW - 2], 1);
+    for (int i = 0; i < W + kMaxW - 1; ++i) xv[i] = 0.f;
+    if (active) {
+#pragma unroll
+        for (int j = 0; j < kNV; ++j) Io<T>::ldv(xr + j * VEC, reinterpret_cast<float(&)[VEC]>(xv[kMaxW - 1 + j * VEC]));
+    }
+    // halo: last 3 elements of the previous thread of the same row
+    const float h0 = __shfl_up_sync(0xffffffffu, xv[W + kMaxW - 4], 1);
+    const float h1 = __shfl_up_sync(0xffffffffu, xv[W + kMaxW - 3], 1);
+    const float h2 = __shfl_up_sync(0xffffffffu, xv[W + kMaxW - 2], 1);
     if (active && v > 0) {
         if (lane > 0) {
             xv[0] = h0; xv[1] = h1; xv[2] = h2;
         } else {
-            xv[0] = Io<T>::ld(xr + v * VEC - 3);
-            xv[1] = Io<T>::ld(xr + v * VEC - 2);
-            xv[2] = Io<T>::ld(xr + v * VEC - 1);
+            xv[0] = Io<T>::ld(xr - 3);
+            xv[1] = Io<T>::ld(xr - 2);
+            xv[2] = Io<T>::ld(xr - 1);
         }
     }
     if (!active) return;
@@ -67,15 +73,19 @@ __global__ void __launch_bounds__(256) conv_fwd_vec_kernel(const ConvArgs a) {
         w[i] = wi >= 0 ? load_w(a.weight, a.w_dtype, d * a.w_ds + wi * a.w_ws) : 0.f;
     }
     const float bias = a.bias != nullptr ? load_w(a.bias, a.w_dtype, d) : 0.f;
-    float ov[VEC];
+    T *orow = reinterpret_cast<T *>(a.out) + b * a.o_bs + d * a.o_ds + v * W;
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-        float acc = bias;
+    for (int j = 0; j < kNV; ++j) {
+        float ov[VEC];
 #pragma unroll
-        for (int k = 0; k < kMaxW; ++k) acc = fmaf(w[k], xv[i + k], acc);
-        ov[i] = a.silu ? silu_f(acc) : acc;
+        for (int i = 0; i < VEC; ++i) {
+            float acc = bias;
+#pragma unroll
+            for (int k = 0; k < kMaxW; ++k) acc = fmaf(w[k], xv[j * VEC + i + k], acc);
+            ov[i] = a.silu ? silu_t<sizeof(T) == 2>(acc) : acc;
+        }
+        Io<T>::stv(orow + j * VEC, ov);
     }
-    Io<T>::stv(reinterpret_cast<T *>(a.out) + b * a.o_bs + d * a.o_ds + v * VEC, ov);
 }
 
 // scalar / gathered path: one thread per output element, x read through the optional token order
@@ -256,8 +266,14 @@ __global__ void __launch_bounds__(kBwdThreads) conv_bwd_kernel(const ConvArgs a)
 template <typename T>
 int run_fwd(const ConvArgs &a, bool vec_ok, cudaStream_t stream) {
     if (vec_ok && a.perm == nullptr) {
-        const int64_t total = (int64_t)a.batch * a.dim * (a.seqlen / Io<T>::kVec);
-        conv_fwd_vec_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(a);
+        const int vpr = a.seqlen / Io<T>::kVec;
+        if (vpr % 2 == 0) {
+            const int64_t total = (int64_t)a.batch * a.dim * (vpr / 2);
+            conv_fwd_vec_kernel<T, 2><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(a);
+        } else {
+            const int64_t total = (int64_t)a.batch * a.dim * vpr;
+            conv_fwd_vec_kernel<T, 1><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(a);
+        }
     } else {
         const int64_t total = (int64_t)a.batch * a.dim * a.seqlen;
         conv_fwd_scalar_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(a);

@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(kRows, 3) scan_fwd_kernel(const ScanFwdArgs a)
 #pragma unroll
             for (int k = 0; k < VEC; ++k) {
                 dv[k] += bias;
-                if (kSoftplus) dv[k] = softplus_f(dv[k]);
+                if (kSoftplus) dv[k] = softplus_t<sizeof(T) == 2>(dv[k]);
                 if (kMask && l0 + j + k >= L) {            // identity step past the end keeps the final state exact
                     dv[k] = 0.f;                           // (tile columns past L are never filled: do not trust them)
                     uv[k] = 0.f;
@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(kRows, 3) scan_fwd_kernel(const ScanFwdArgs a)
                 }
                 const float2 y2 = add2(ya, yb);
                 yv[k] = fmaf(Dv, uv[k], y2.x + y2.y);
-                gv[k] = kHasZ ? yv[k] * silu_f(zv[k]) : yv[k];
+                gv[k] = kHasZ ? yv[k] * silu_t<sizeof(T) == 2>(zv[k]) : yv[k];
             }
             // in place: gated output over u, pre-gate output (training only) over delta
             Io<T>::stv(reinterpret_cast<T *>(&s.u[st][tid][0]) + j, gv);
