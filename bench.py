@@ -187,10 +187,20 @@ def run_b200(args, rank, local_rank, world):
     timed_call.on = False
     _lib.call = timed_call
 
-    def step(x, i):
+    def eager_step(x, i):
         with torch.no_grad(), autocast:
             v = model.forward_with_cfg(x, ones * ts[i], yy, cfg_scale=CFG_SCALE)
         return x + (ts[i + 1] - ts[i]) * v.float()
+
+    graphed = None
+    if not args.no_graph:
+        from dimsum_b200.sampler import GraphedCfgStep
+        graphed = GraphedCfgStep(model, x0, yy, CFG_SCALE, torch.bfloat16 if args.dtype == "bf16" else None)
+
+    def step(x, i):
+        if graphed is None:
+            return eager_step(x, i)
+        return x + (ts[i + 1] - ts[i]) * graphed(x, ones * ts[i]).float()
 
     def barrier():
         if world > 1:
@@ -214,9 +224,20 @@ def run_b200(args, rank, local_rank, world):
         barrier()
         timed_call.on = False
     launches = _lib.launch_count() - launches0
+    if graphed is not None:
+        launches = graphed.launches_per_replay * args.steps     # replays do not pass through the C-ABI counter
     ms = ev0.elapsed_time(ev1) / args.steps
-    scan_ms = sum(s.elapsed_time(e) for s, e in scan_events) / max(1, len(scan_events))
     assert torch.isfinite(x).all()
+    if graphed is not None:
+        # per-kernel CUDA events cannot ride inside a graph replay: time the scan launches in an instrumented eager
+        # pass over the same inputs, right after the timed region
+        timed_call.on = True
+        xe = x0.clone()
+        for i in range(min(args.steps, 3)):
+            xe = eager_step(xe, i)
+        torch.cuda.synchronize()
+        timed_call.on = False
+    scan_ms = sum(s.elapsed_time(e) for s, e in scan_events) / max(1, len(scan_events))
 
     # ------------------------------------------------------------------ end to end: host buffers in, host buffers out
     for i in range(min(2, args.warmup)):
@@ -229,8 +250,12 @@ def run_b200(args, rank, local_rank, world):
         xd = x_host.to(dev, non_blocking=True)
         yd = y_host.to(dev, non_blocking=True)
         td = t_host.to(dev, non_blocking=True)
-        with torch.no_grad(), autocast:
-            v = model.forward_with_cfg(xd, td, yd, cfg_scale=CFG_SCALE)
+        if graphed is not None:
+            graphed.y.copy_(yd, non_blocking=True)
+            v = graphed(xd, td)
+        else:
+            with torch.no_grad(), autocast:
+                v = model.forward_with_cfg(xd, td, yd, cfg_scale=CFG_SCALE)
         out_host.copy_(xd + (1.0 / (NUM_GRID - 1)) * v.float(), non_blocking=True)
     e1.record()
     barrier()
@@ -265,6 +290,8 @@ def run_b200(args, rank, local_rank, world):
                                    "over the ranks, 2x rows with CFG, one Euler step of the 250-point grid per step",
                        "latents_total": n_total, "rows_per_rank": 2 * n, "tokens": SEQ, "d_inner": D_INNER, "d_state": D_STATE,
                        "cfg_scale": CFG_SCALE, "matmul": "tf32" if args.dtype == "fp32" else "bf16 autocast",
+                       "launch": "eager" if graphed is None else "CUDA graph replay (%d launches of this repo's kernels per step)"
+                                 % graphed.launches_per_replay,
                        "l2": "working set per step >> 126 MB L2 (xz alone is %.0f MB per mixer call)" % (2 * n * 2048 * 256 * s / 1e6),
                        "params": sum(p.numel() for p in model.parameters())},
             "e2e": {"value": n_total / (ms_e2e * 1e-3), "unit": "latents/s", "ms_per_step": ms_e2e,
@@ -275,6 +302,7 @@ def run_b200(args, rank, local_rank, world):
                          "achieved": achieved, "peak": peak, "peak_source": how + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes_per_launch": by,
                          "avg_launch_ms": scan_ms, "launches_timed": len(scan_events),
+                         "timed_in": "timed region" if graphed is None else "instrumented eager pass right after the timed region",
                          "share_of_step": scan_ms * 32 / ms},
             "clocks": clocks.summary(),
         }
@@ -301,6 +329,7 @@ def main():
     ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--latents", type=int, default=TOTAL_LATENTS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying a CUDA graph")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))

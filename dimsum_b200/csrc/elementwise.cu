@@ -7,36 +7,41 @@
 namespace dimsum {
 namespace {
 
-template <typename T, bool kGate>
+// kNV consecutive 16-byte vectors per thread: all loads are issued before any arithmetic (bytes in flight per thread).
+template <typename T, bool kGate, int kNV>
 __global__ void __launch_bounds__(256) rowwise_kernel(const dimsum_rowwise_params p) {
     constexpr int VEC = Io<T>::kVec;
-    const int vpt = (int)(p.channels / VEC);
+    const int tpt = (int)(p.channels / (VEC * kNV));          // threads per token row
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t total = p.batch * p.seqlen * vpt;
+    const int64_t total = p.batch * p.seqlen * tpt;
     if (gid >= total) return;
-    const int v = (int)(gid % vpt);
-    const int64_t t = gid / vpt;
+    const int v = (int)(gid % tpt);
+    const int64_t t = gid / tpt;
     const int l = (int)(t % p.seqlen);
     const int64_t b = t / p.seqlen;
     const int src_l = p.idx != nullptr ? p.idx[l] : l;
-    const int c0 = v * VEC;
-    float a[VEC], o[VEC];
+    const int c0 = v * VEC * kNV;
+    float a[kNV][VEC], q[kNV][VEC], r[kNV][VEC], o[VEC];
     if (!kGate) {
-        float sh[VEC], sc[VEC];
-        Io<T>::ldv(reinterpret_cast<const T *>(p.x) + b * p.x_batch_stride + (int64_t)src_l * p.x_token_stride + c0, a);
-        Io<T>::ldv(reinterpret_cast<const T *>(p.shift) + b * p.vec_row_stride + c0, sh);
-        Io<T>::ldv(reinterpret_cast<const T *>(p.scale) + b * p.vec_row_stride + c0, sc);
+        const T *xp = reinterpret_cast<const T *>(p.x) + b * p.x_batch_stride + (int64_t)src_l * p.x_token_stride + c0;
+        const T *sh = reinterpret_cast<const T *>(p.shift) + b * p.vec_row_stride + c0;
+        const T *sc = reinterpret_cast<const T *>(p.scale) + b * p.vec_row_stride + c0;
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) o[i] = fmaf(a[i], 1.f + sc[i], sh[i]);
+        for (int j = 0; j < kNV; ++j) { Io<T>::ldv(xp + j * VEC, a[j]); Io<T>::ldv(sh + j * VEC, q[j]); Io<T>::ldv(sc + j * VEC, r[j]); }
     } else {
-        float m[VEC], g[VEC];
-        Io<T>::ldv(reinterpret_cast<const T *>(p.x) + b * p.x_batch_stride + (int64_t)l * p.x_token_stride + c0, a);
-        Io<T>::ldv(reinterpret_cast<const T *>(p.m) + b * p.m_batch_stride + (int64_t)src_l * p.m_token_stride + c0, m);
-        Io<T>::ldv(reinterpret_cast<const T *>(p.gate) + b * p.vec_row_stride + c0, g);
+        const T *xp = reinterpret_cast<const T *>(p.x) + b * p.x_batch_stride + (int64_t)l * p.x_token_stride + c0;
+        const T *mp = reinterpret_cast<const T *>(p.m) + b * p.m_batch_stride + (int64_t)src_l * p.m_token_stride + c0;
+        const T *gp = reinterpret_cast<const T *>(p.gate) + b * p.vec_row_stride + c0;
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) o[i] = fmaf(g[i], m[i], a[i]);
+        for (int j = 0; j < kNV; ++j) { Io<T>::ldv(xp + j * VEC, a[j]); Io<T>::ldv(mp + j * VEC, q[j]); Io<T>::ldv(gp + j * VEC, r[j]); }
     }
-    Io<T>::stv(reinterpret_cast<T *>(p.dst) + b * p.dst_batch_stride + (int64_t)l * p.dst_token_stride + c0, o);
+    T *dp = reinterpret_cast<T *>(p.dst) + b * p.dst_batch_stride + (int64_t)l * p.dst_token_stride + c0;
+#pragma unroll
+    for (int j = 0; j < kNV; ++j) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) o[i] = kGate ? fmaf(r[j][i], q[j][i], a[j][i]) : fmaf(a[j][i], 1.f + r[j][i], q[j][i]);
+        Io<T>::stv(dp + j * VEC, o);
+    }
 }
 
 // one warp per row; the row lives in registers between the two passes (channels <= 32 * 16 * VEC per warp loop)
@@ -99,21 +104,25 @@ DEV float gelu_tanh_f(float x) {
     return 0.5f * x * (1.f + t);
 }
 
-template <typename T>
+template <typename T, int kNV>
 __global__ void __launch_bounds__(256) gelu_mul_kernel(const dimsum_gelu_mul_params p) {
     constexpr int VEC = Io<T>::kVec;
-    const int vpr = (int)(p.hidden / VEC);
+    const int tpr = (int)(p.hidden / (VEC * kNV));
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= p.rows * vpr) return;
-    const int v = (int)(gid % vpr);
-    const int64_t r = gid / vpr;
-    const T *x = reinterpret_cast<const T *>(p.x) + r * p.x_row_stride;
-    float a[VEC], b[VEC], o[VEC];
-    Io<T>::ldv(x + v * VEC, a);
-    Io<T>::ldv(x + p.hidden + v * VEC, b);
+    if (gid >= p.rows * tpr) return;
+    const int v = (int)(gid % tpr);
+    const int64_t r = gid / tpr;
+    const T *x = reinterpret_cast<const T *>(p.x) + r * p.x_row_stride + v * VEC * kNV;
+    float a[kNV][VEC], b[kNV][VEC], o[VEC];
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) o[i] = gelu_tanh_f(a[i]) * b[i];
-    Io<T>::stv(reinterpret_cast<T *>(p.y) + r * p.y_row_stride + v * VEC, o);
+    for (int j = 0; j < kNV; ++j) { Io<T>::ldv(x + j * VEC, a[j]); Io<T>::ldv(x + p.hidden + j * VEC, b[j]); }
+    T *y = reinterpret_cast<T *>(p.y) + r * p.y_row_stride + v * VEC * kNV;
+#pragma unroll
+    for (int j = 0; j < kNV; ++j) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) o[i] = gelu_tanh_f(a[j][i]) * b[j][i];
+        Io<T>::stv(y + j * VEC, o);
+    }
 }
 
 int rowwise_entry(const dimsum_rowwise_params *p, bool gate, void *stream_) {
@@ -132,11 +141,14 @@ int rowwise_entry(const dimsum_rowwise_params *p, bool gate, void *stream_) {
     DIMSUM_REQUIRE(ok, DIMSUM_ERR_UNSUPPORTED, "%s: rows must be 16-byte aligned multiples of 16 bytes", who);
     DIMSUM_REQUIRE(p->dst != p->x || p->idx == nullptr || gate, DIMSUM_ERR_INVALID, "%s: in-place gather is not supported", who);
     if (p->batch == 0) return DIMSUM_OK;
-    const int64_t total = p->batch * p->seqlen * (p->channels / vec);
+    const int nv = (p->channels / vec) % 2 == 0 ? 2 : 1;
+    const int64_t total = p->batch * p->seqlen * (p->channels / (vec * nv));
     const unsigned blocks = (unsigned)((total + 255) / 256);
-#define LAUNCH(T)                                                                   \
-    if (gate) rowwise_kernel<T, true><<<blocks, 256, 0, stream>>>(*p);              \
-    else rowwise_kernel<T, false><<<blocks, 256, 0, stream>>>(*p);
+#define LAUNCH(T)                                                                                       \
+    if (gate) { if (nv == 2) rowwise_kernel<T, true, 2><<<blocks, 256, 0, stream>>>(*p);                \
+                else rowwise_kernel<T, true, 1><<<blocks, 256, 0, stream>>>(*p); }                      \
+    else { if (nv == 2) rowwise_kernel<T, false, 2><<<blocks, 256, 0, stream>>>(*p);                    \
+           else rowwise_kernel<T, false, 1><<<blocks, 256, 0, stream>>>(*p); }
     if (p->dtype == DIMSUM_F32) { LAUNCH(float) }
     else if (p->dtype == DIMSUM_BF16) { LAUNCH(__nv_bfloat16) }
     else { LAUNCH(__half) }
@@ -179,10 +191,15 @@ extern "C" int dimsum_gelu_mul(const dimsum_gelu_mul_params *p, void *stream_) {
     DIMSUM_REQUIRE(p->hidden % vec == 0 && aligned16(p->x) && aligned16(p->y) && p->x_row_stride % vec == 0 &&
                        p->y_row_stride % vec == 0, DIMSUM_ERR_UNSUPPORTED, "gelu_mul: rows must be 16-byte aligned");
     if (p->rows == 0) return DIMSUM_OK;
-    const int64_t total = p->rows * (p->hidden / vec);
+    const bool two = (p->hidden / vec) % 2 == 0;
+    const int64_t total = p->rows * (p->hidden / (vec * (two ? 2 : 1)));
     const unsigned blocks = (unsigned)((total + 255) / 256);
-    if (p->dtype == DIMSUM_F32) gelu_mul_kernel<float><<<blocks, 256, 0, stream>>>(*p);
-    else if (p->dtype == DIMSUM_BF16) gelu_mul_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(*p);
-    else gelu_mul_kernel<__half><<<blocks, 256, 0, stream>>>(*p);
+#define GM(T)                                                                       \
+    if (two) gelu_mul_kernel<T, 2><<<blocks, 256, 0, stream>>>(*p);                 \
+    else gelu_mul_kernel<T, 1><<<blocks, 256, 0, stream>>>(*p);
+    if (p->dtype == DIMSUM_F32) { GM(float) }
+    else if (p->dtype == DIMSUM_BF16) { GM(__nv_bfloat16) }
+    else { GM(__half) }
+#undef GM
     return check_launch("gelu_mul");
 }

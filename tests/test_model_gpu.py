@@ -87,5 +87,8 @@ def test_fixed_seed_cfg_sampling_matches_oracle_sampler():
         with torch.no_grad():
             want = ref_model.euler_sample_oracle(sd, z, y, 4.0, num_steps=steps, null_class=10)
         assert rel_err(got, want) <= 1e-4, rel_err(got, want)
+        # CUDA-graph replay of the same evaluation gives the same latents
+        got_g = sample_cfg(m, z.cuda(), y.cuda(), cfg_scale=4.0, num_steps=steps, use_graph=True)
+        assert rel_err(got_g, got) <= 1e-6
     finally:
         torch.backends.cuda.matmul.allow_tf32 = old
