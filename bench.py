@@ -59,6 +59,13 @@ class ClockSampler:
 
     def __init__(self, gpu_index):
         self.rows, self.proc, self.idx = [], None, gpu_index
+        self.t0 = self.t1 = None
+
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def __enter__(self):
         try:
@@ -72,7 +79,7 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append([time.time()] + [c.strip() for c in line.split(",")])
 
     def __exit__(self, *exc):
         if self.proc is not None:
@@ -84,12 +91,19 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self):
-        sm = sorted(int(float(r[1])) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
-        if not sm:
+        rows = [r[1:] for r in self.rows if len(r) >= 10 and r[2].replace(".", "").isdigit()
+                and (self.t0 is None or self.t0 <= r[0] <= (self.t1 or r[0]) + 0.15)]
+        window = "timed region"
+        if not rows:   # region shorter than the sampling period: fall back to everything sampled while the process ran
+            rows = [r[1:] for r in self.rows if len(r) >= 10 and r[2].replace(".", "").isdigit()]
+            window = "whole run (timed region shorter than the 100 ms sampling period)"
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(float(r[1])) for r in rows)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(float(self.rows[0][2])), "reasons": reasons, "samples": len(sm)}
+        reasons = sorted({n for r in rows for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(float(rows[0][2])), "reasons": reasons, "samples": len(sm),
+                "window": window}
 
 
 def measured_peak():
@@ -208,20 +222,22 @@ def run_b200(args, rank, local_rank, world):
         torch.cuda.synchronize()
 
     # ------------------------------------------------------------------ device-resident timing
-    x = x0.clone()
-    for i in range(args.warmup):
-        x = step(x, i)
-    barrier()
-    launches0 = _lib.launch_count()
-    with ClockSampler(local_rank) as clocks:
+    with ClockSampler(local_rank) as clocks:       # nvidia-smi is started before the warm-up so it is sampling by the time
+        x = x0.clone()                             # the timed region starts; only samples inside the region are reported
+        for i in range(args.warmup):
+            x = step(x, i)
+        barrier()
+        launches0 = _lib.launch_count()
         timed_call.on = True
         barrier()
+        clocks.mark_start()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         for i in range(args.steps):
             x = step(x, args.warmup + i)
         ev1.record()
         barrier()
+        clocks.mark_end()
         timed_call.on = False
     launches = _lib.launch_count() - launches0
     if graphed is not None:
