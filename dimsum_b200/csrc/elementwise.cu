@@ -7,11 +7,34 @@
 namespace dimsum {
 namespace {
 
-// kNV consecutive 16-byte vectors per thread: all loads are issued before any arithmetic (bytes in flight per thread).
-template <typename T, bool kGate, int kNV>
+// 8 consecutive channels of a tensor whose dtype is only known at run time (uniform branch): 32 B (fp32) or 16 B.
+DEV void ld8(const void *base, int dtype, int64_t idx, float (&v)[8]) {
+    if (dtype == DIMSUM_F32) {
+        const float *p = reinterpret_cast<const float *>(base) + idx;
+        Io<float>::ldv(p, reinterpret_cast<float(&)[4]>(v[0]));
+        Io<float>::ldv(p + 4, reinterpret_cast<float(&)[4]>(v[4]));
+    } else if (dtype == DIMSUM_BF16) {
+        Io<__nv_bfloat16>::ldv(reinterpret_cast<const __nv_bfloat16 *>(base) + idx, v);
+    } else {
+        Io<__half>::ldv(reinterpret_cast<const __half *>(base) + idx, v);
+    }
+}
+DEV void st8(void *base, int dtype, int64_t idx, const float (&v)[8]) {
+    if (dtype == DIMSUM_F32) {
+        float *p = reinterpret_cast<float *>(base) + idx;
+        Io<float>::stv(p, reinterpret_cast<const float(&)[4]>(v[0]));
+        Io<float>::stv(p + 4, reinterpret_cast<const float(&)[4]>(v[4]));
+    } else if (dtype == DIMSUM_BF16) {
+        Io<__nv_bfloat16>::stv(reinterpret_cast<__nv_bfloat16 *>(base) + idx, v);
+    } else {
+        Io<__half>::stv(reinterpret_cast<__half *>(base) + idx, v);
+    }
+}
+
+// one thread = 8 consecutive channels of one token; all loads are issued before the arithmetic
+template <bool kGate>
 __global__ void __launch_bounds__(256) rowwise_kernel(const dimsum_rowwise_params p) {
-    constexpr int VEC = Io<T>::kVec;
-    const int tpt = (int)(p.channels / (VEC * kNV));          // threads per token row
+    const int tpt = (int)(p.channels / 8);                    // threads per token row
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t total = p.batch * p.seqlen * tpt;
     if (gid >= total) return;
@@ -20,28 +43,22 @@ __global__ void __launch_bounds__(256) rowwise_kernel(const dimsum_rowwise_param
     const int l = (int)(t % p.seqlen);
     const int64_t b = t / p.seqlen;
     const int src_l = p.idx != nullptr ? p.idx[l] : l;
-    const int c0 = v * VEC * kNV;
-    float a[kNV][VEC], q[kNV][VEC], r[kNV][VEC], o[VEC];
+    const int c0 = v * 8;
+    float a[8], q[8], r[8], o[8];
     if (!kGate) {
-        const T *xp = reinterpret_cast<const T *>(p.x) + b * p.x_batch_stride + (int64_t)src_l * p.x_token_stride + c0;
-        const T *sh = reinterpret_cast<const T *>(p.shift) + b * p.vec_row_stride + c0;
-        const T *sc = reinterpret_cast<const T *>(p.scale) + b * p.vec_row_stride + c0;
+        ld8(p.x, (int)p.x_dtype, b * p.x_batch_stride + (int64_t)src_l * p.x_token_stride + c0, a);
+        ld8(p.shift, (int)p.aux_dtype, b * p.vec_row_stride + c0, q);
+        ld8(p.scale, (int)p.aux_dtype, b * p.vec_row_stride + c0, r);
 #pragma unroll
-        for (int j = 0; j < kNV; ++j) { Io<T>::ldv(xp + j * VEC, a[j]); Io<T>::ldv(sh + j * VEC, q[j]); Io<T>::ldv(sc + j * VEC, r[j]); }
+        for (int i = 0; i < 8; ++i) o[i] = fmaf(a[i], 1.f + r[i], q[i]);
     } else {
-        const T *xp = reinterpret_cast<const T *>(p.x) + b * p.x_batch_stride + (int64_t)l * p.x_token_stride + c0;
-        const T *mp = reinterpret_cast<const T *>(p.m) + b * p.m_batch_stride + (int64_t)src_l * p.m_token_stride + c0;
-        const T *gp = reinterpret_cast<const T *>(p.gate) + b * p.vec_row_stride + c0;
+        ld8(p.x, (int)p.x_dtype, b * p.x_batch_stride + (int64_t)l * p.x_token_stride + c0, a);
+        ld8(p.m, (int)p.aux_dtype, b * p.m_batch_stride + (int64_t)src_l * p.m_token_stride + c0, q);
+        ld8(p.gate, (int)p.aux_dtype, b * p.vec_row_stride + c0, r);
 #pragma unroll
-        for (int j = 0; j < kNV; ++j) { Io<T>::ldv(xp + j * VEC, a[j]); Io<T>::ldv(mp + j * VEC, q[j]); Io<T>::ldv(gp + j * VEC, r[j]); }
+        for (int i = 0; i < 8; ++i) o[i] = fmaf(r[i], q[i], a[i]);
     }
-    T *dp = reinterpret_cast<T *>(p.dst) + b * p.dst_batch_stride + (int64_t)l * p.dst_token_stride + c0;
-#pragma unroll
-    for (int j = 0; j < kNV; ++j) {
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) o[i] = kGate ? fmaf(r[j][i], q[j][i], a[j][i]) : fmaf(a[j][i], 1.f + r[j][i], q[j][i]);
-        Io<T>::stv(dp + j * VEC, o);
-    }
+    st8(p.dst, (int)p.dst_dtype, b * p.dst_batch_stride + (int64_t)l * p.dst_token_stride + c0, o);
 }
 
 // one warp per row; the row lives in registers between the two passes (channels <= 32 * 16 * VEC per warp loop)
@@ -131,28 +148,20 @@ int rowwise_entry(const dimsum_rowwise_params *p, bool gate, void *stream_) {
     DIMSUM_REQUIRE(p != nullptr && p->x && p->dst, DIMSUM_ERR_INVALID, "%s: null pointer", who);
     DIMSUM_REQUIRE(gate ? (p->m && p->gate) : (p->shift && p->scale), DIMSUM_ERR_INVALID, "%s: null operand", who);
     DIMSUM_REQUIRE(p->batch >= 0 && p->seqlen > 0 && p->channels > 0, DIMSUM_ERR_INVALID, "%s: bad sizes", who);
-    DIMSUM_REQUIRE(p->dtype >= 0 && p->dtype <= 2, DIMSUM_ERR_INVALID, "%s: unknown dtype", who);
-    const int vec = p->dtype == DIMSUM_F32 ? 4 : 8;
-    bool ok = p->channels % vec == 0 && aligned16(p->x) && aligned16(p->dst) && p->x_batch_stride % vec == 0 &&
-              p->x_token_stride % vec == 0 && p->dst_batch_stride % vec == 0 && p->dst_token_stride % vec == 0 &&
-              p->vec_row_stride % vec == 0;
-    if (gate) ok = ok && aligned16(p->m) && aligned16(p->gate) && p->m_batch_stride % vec == 0 && p->m_token_stride % vec == 0;
+    auto dt_ok = [](int64_t d) { return d >= 0 && d <= 2; };
+    DIMSUM_REQUIRE(dt_ok(p->x_dtype) && dt_ok(p->aux_dtype) && dt_ok(p->dst_dtype), DIMSUM_ERR_INVALID, "%s: unknown dtype", who);
+    bool ok = p->channels % 8 == 0 && aligned16(p->x) && aligned16(p->dst) && p->x_batch_stride % 8 == 0 &&
+              p->x_token_stride % 8 == 0 && p->dst_batch_stride % 8 == 0 && p->dst_token_stride % 8 == 0 &&
+              p->vec_row_stride % 8 == 0;
+    if (gate) ok = ok && aligned16(p->m) && aligned16(p->gate) && p->m_batch_stride % 8 == 0 && p->m_token_stride % 8 == 0;
     else ok = ok && aligned16(p->shift) && aligned16(p->scale);
-    DIMSUM_REQUIRE(ok, DIMSUM_ERR_UNSUPPORTED, "%s: rows must be 16-byte aligned multiples of 16 bytes", who);
+    DIMSUM_REQUIRE(ok, DIMSUM_ERR_UNSUPPORTED, "%s: rows must be 16-byte aligned and channels a multiple of 8", who);
     DIMSUM_REQUIRE(p->dst != p->x || p->idx == nullptr || gate, DIMSUM_ERR_INVALID, "%s: in-place gather is not supported", who);
     if (p->batch == 0) return DIMSUM_OK;
-    const int nv = (p->channels / vec) % 2 == 0 ? 2 : 1;
-    const int64_t total = p->batch * p->seqlen * (p->channels / (vec * nv));
+    const int64_t total = p->batch * p->seqlen * (p->channels / 8);
     const unsigned blocks = (unsigned)((total + 255) / 256);
-#define LAUNCH(T)                                                                                       \
-    if (gate) { if (nv == 2) rowwise_kernel<T, true, 2><<<blocks, 256, 0, stream>>>(*p);                \
-                else rowwise_kernel<T, true, 1><<<blocks, 256, 0, stream>>>(*p); }                      \
-    else { if (nv == 2) rowwise_kernel<T, false, 2><<<blocks, 256, 0, stream>>>(*p);                    \
-           else rowwise_kernel<T, false, 1><<<blocks, 256, 0, stream>>>(*p); }
-    if (p->dtype == DIMSUM_F32) { LAUNCH(float) }
-    else if (p->dtype == DIMSUM_BF16) { LAUNCH(__nv_bfloat16) }
-    else { LAUNCH(__half) }
-#undef LAUNCH
+    if (gate) rowwise_kernel<true><<<blocks, 256, 0, stream>>>(*p);
+    else rowwise_kernel<false><<<blocks, 256, 0, stream>>>(*p);
     return check_launch(who);
 }
 

@@ -17,8 +17,8 @@ def _rows(t, name):
 
 
 def _vec(t, ref, name):
-    if t.dim() != 2 or t.stride(1) != 1 or t.shape != (ref.shape[0], ref.shape[2]) or t.dtype != ref.dtype:
-        raise RuntimeError(f"{name} must be (batch, channels) with stride(1) == 1 and the dtype of x")
+    if t.dim() != 2 or t.stride(1) != 1 or t.shape != (ref.shape[0], ref.shape[2]) or t.dtype not in _DT:
+        raise RuntimeError(f"{name} must be (batch, channels) with stride(1) == 1")
 
 
 def _idx(idx, L):
@@ -29,15 +29,16 @@ def _idx(idx, L):
     return idx.data_ptr()
 
 
-def modulate(x, shift, scale, idx=None):
-    """out[b, l] = x[b, idx[l]] * (1 + scale[b]) + shift[b]"""
+def modulate(x, shift, scale, idx=None, out_dtype=None):
+    """out[b, l] = x[b, idx[l]] * (1 + scale[b]) + shift[b];  x, shift/scale and out may have different dtypes."""
     _rows(x, "x"); _vec(shift, x, "shift"); _vec(scale, x, "scale")
-    if shift.stride(0) != scale.stride(0):
-        raise RuntimeError("shift and scale must share their row stride (chunks of one adaLN output)")
-    out = torch.empty(x.shape, device=x.device, dtype=x.dtype)
+    if shift.stride(0) != scale.stride(0) or shift.dtype != scale.dtype:
+        raise RuntimeError("shift and scale must share dtype and row stride (chunks of one adaLN output)")
+    out = torch.empty(x.shape, device=x.device, dtype=out_dtype or x.dtype)
     with torch.cuda.device(x.device):
         p = _lib.RowwiseParams()
-        p.batch, p.seqlen, p.channels, p.dtype = x.shape[0], x.shape[1], x.shape[2], _DT[x.dtype]
+        p.batch, p.seqlen, p.channels = x.shape
+        p.x_dtype, p.aux_dtype, p.dst_dtype = _DT[x.dtype], _DT[shift.dtype], _DT[out.dtype]
         p.x_batch_stride, p.x_token_stride = x.stride(0), x.stride(1)
         p.dst_batch_stride, p.dst_token_stride = out.stride(0), out.stride(1)
         p.vec_row_stride = shift.stride(0)
@@ -47,15 +48,16 @@ def modulate(x, shift, scale, idx=None):
     return out
 
 
-def gate_residual(x, gate, m, idx=None):
-    """out[b, l] = x[b, l] + gate[b] * m[b, idx[l]]"""
+def gate_residual(x, gate, m, idx=None, out_dtype=None):
+    """out[b, l] = x[b, l] + gate[b] * m[b, idx[l]]; gate and m share a dtype that may differ from x's and the output's."""
     _rows(x, "x"); _rows(m, "m"); _vec(gate, x, "gate")
-    if m.shape != x.shape or m.dtype != x.dtype:
-        raise RuntimeError("m must match x")
-    out = torch.empty(x.shape, device=x.device, dtype=x.dtype)
+    if m.shape != x.shape or m.dtype != gate.dtype:
+        raise RuntimeError("m must have the shape of x and the dtype of gate")
+    out = torch.empty(x.shape, device=x.device, dtype=out_dtype or x.dtype)
     with torch.cuda.device(x.device):
         p = _lib.RowwiseParams()
-        p.batch, p.seqlen, p.channels, p.dtype = x.shape[0], x.shape[1], x.shape[2], _DT[x.dtype]
+        p.batch, p.seqlen, p.channels = x.shape
+        p.x_dtype, p.aux_dtype, p.dst_dtype = _DT[x.dtype], _DT[m.dtype], _DT[out.dtype]
         p.x_batch_stride, p.x_token_stride = x.stride(0), x.stride(1)
         p.m_batch_stride, p.m_token_stride = m.stride(0), m.stride(1)
         p.dst_batch_stride, p.dst_token_stride = out.stride(0), out.stride(1)

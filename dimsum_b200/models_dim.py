@@ -40,14 +40,20 @@ def _fused_ok(x):
 
 def _mod(x, shift, scale, idx=None):
     if _fused_ok(x):
-        return fused.modulate(x, shift.to(x.dtype), scale.to(x.dtype), idx)
+        # under autocast the consumer is a low-precision GEMM: emit its input dtype directly (no separate cast pass)
+        out_dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else None
+        return fused.modulate(x, shift, scale, idx, out_dtype=out_dtype)
     assert idx is None
     return modulate(x, shift, scale)
 
 
-def _gated(x, gate, m, idx=None):
+def _gated(x, gate, m, idx=None, feeds_gemm=False):
     if _fused_ok(x):
-        return fused.gate_residual(x, gate.to(x.dtype), m.to(x.dtype), idx)
+        if m.dtype != gate.dtype:
+            m = m.to(gate.dtype)
+        # a result that only feeds low-precision GEMMs under autocast is emitted in their dtype (no cast pass)
+        out_dtype = torch.get_autocast_dtype("cuda") if feeds_gemm and torch.is_autocast_enabled() else None
+        return fused.gate_residual(x, gate, m, idx, out_dtype=out_dtype)
     assert idx is None
     return x + gate.unsqueeze(1) * m
 
@@ -195,7 +201,7 @@ class DiMBlockRaw(nn.Module):
         if _fused_ok(x):
             # the scan order rides on the row index of the two glue kernels: no permuted copy, no extra pass
             m = self.mixer(_mod(x, shift, scale, self._order), c)
-            return _gated(x, gate, m, self._inv)
+            return _gated(x, gate, m, self._inv, feeds_gemm=True)
         return x + gate.unsqueeze(1) * self.mixer(modulate(x, shift, scale), c, order=self._order)
 
 
@@ -222,7 +228,7 @@ class WaveDiMBlock(nn.Module):
     def forward(self, x, c):
         h = wavelet_packet(x, self._pos)                                 # _dwt_fast + local_scan
         shift, scale, gate = self.adaLN_modulation(c).chunk(3, dim=1)
-        h = _gated(h, gate, self.mixer(_mod(h, shift, scale), c))
+        h = _gated(h, gate, self.mixer(_mod(h, shift, scale), c), feeds_gemm=True)
         return wavelet_packet_inverse(h, self._pos)                      # local_reverse + _idwt_fast
 
 

@@ -183,10 +183,13 @@ int dimsum_wavelet_packet_inv(const dimsum_wavelet_params *p, void *stream);
  * modulate      : dst[b, l, :] = x[b, idx[l], :] * (1 + scale[b, :]) + shift[b, :]          (models_dim.py:34-35 + order)
  * gate_residual : dst[b, l, :] = x[b, l, :] + gate[b, :] * m[b, idx[l], :]                  (models_dim.py:1510-1512 + un-order)
  * x, m, dst: (batch, seqlen, channels) with channel stride 1; shift/scale/gate: (batch, channels) with a row stride
- * (they are chunks of one adaLN GEMM output).  idx: NULL or int32[seqlen].  All tensors share `dtype`.
+ * (they are chunks of one adaLN GEMM output).  idx: NULL or int32[seqlen].  Mixed precision is allowed, as it occurs
+ * under autocast: x_dtype (residual stream, typically fp32), aux_dtype (m, shift, scale, gate: the GEMM outputs) and
+ * dst_dtype are independent; channels % 8 == 0.
  */
 typedef struct {
-    int64_t batch, seqlen, channels, dtype;
+    int64_t batch, seqlen, channels;
+    int64_t x_dtype, aux_dtype, dst_dtype;
     int64_t x_batch_stride, x_token_stride;
     int64_t m_batch_stride, m_token_stride;
     int64_t dst_batch_stride, dst_token_stride;

@@ -26,6 +26,15 @@ def test_modulate_and_gate_residual_with_order(dtype):
     got = fused.gate_residual(x, gate, m, inv.to(torch.int32))
     assert rel_err(got, want) <= (1e-6 if dtype == torch.float32 else 1e-2)
     assert torch.equal(fused.modulate(x, shift, scale), fused.modulate(x.contiguous(), shift, scale))
+    # mixed precision as it occurs under autocast: fp32 residual stream, bf16 adaLN / branch outputs, bf16 GEMM input
+    xf, ab = hidden.float()[:, :, C:], ada.bfloat16()
+    sh, sc, gt = ab.chunk(3, dim=1)
+    got = fused.modulate(xf, sh, sc, order.to(torch.int32), out_dtype=torch.bfloat16)
+    want = (xf * (1 + sc.float().unsqueeze(1)) + sh.float().unsqueeze(1))[:, order]
+    assert got.dtype == torch.bfloat16 and rel_err(got, want) <= 1e-2
+    got = fused.gate_residual(xf, gt, m.bfloat16(), inv.to(torch.int32))
+    want = xf + gt.float().unsqueeze(1) * m.bfloat16().float()[:, inv]
+    assert got.dtype == torch.float32 and rel_err(got, want) <= 1e-6
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
