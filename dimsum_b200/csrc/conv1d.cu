@@ -18,7 +18,7 @@ struct ConvArgs {
     float *dweight, *dbias;
     const int32_t *perm;
     int64_t x_bs, x_ds, o_bs, o_ds, g_bs, g_ds, dx_bs, dx_ds, w_ds, w_ws;
-    int batch, dim, seqlen, width, silu, w_dtype, vec_ok;
+    int batch, dim, seqlen, width, silu, w_dtype, vec_ok, out_vec_ok;
 };
 
 DEV float load_w(const void *w, int dtype, int64_t idx) {
@@ -88,25 +88,54 @@ __global__ void __launch_bounds__(256) conv_fwd_vec_kernel(const ConvArgs a) {
     }
 }
 
-// scalar / gathered path: one thread per output element, x read through the optional token order
+// scalar / gathered path.  A thread produces kGW consecutive outputs of one row from kGW + 3 inputs fetched once each
+// through the optional token order (4-byte gathers inside a row that stays in L1), and stores them with one vector
+// write when the row is aligned: ~3x fewer loads than one thread per output.
+constexpr int kGW = 8;
+
 template <typename T>
 __global__ void __launch_bounds__(256) conv_fwd_scalar_kernel(const ConvArgs a) {
+    const int tpr = (a.seqlen + kGW - 1) / kGW;                  // threads per row
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t total = (int64_t)a.batch * a.dim * a.seqlen;
+    const int64_t total = (int64_t)a.batch * a.dim * tpr;
     if (gid >= total) return;
-    const int l = (int)(gid % a.seqlen);
-    const int64_t row = gid / a.seqlen;
+    const int l0 = (int)(gid % tpr) * kGW;
+    const int64_t row = gid / tpr;
     const int d = (int)(row % a.dim);
     const int b = (int)(row / a.dim);
     const T *xr = reinterpret_cast<const T *>(a.x) + b * a.x_bs + d * a.x_ds;
-    float acc = a.bias != nullptr ? load_w(a.bias, a.w_dtype, d) : 0.f;
-    for (int k = 0; k < a.width; ++k) {
-        const int ls = l - (a.width - 1) + k;
-        if (ls < 0) continue;
-        const int tok = a.perm != nullptr ? a.perm[ls] : ls;
-        acc = fmaf(load_w(a.weight, a.w_dtype, d * a.w_ds + k * a.w_ws), Io<T>::ld(xr + tok), acc);
+    float xs[kGW + kMaxW - 1];
+#pragma unroll
+    for (int i = 0; i < kGW + kMaxW - 1; ++i) {
+        const int ls = l0 - (kMaxW - 1) + i;
+        float v = 0.f;
+        if (ls >= 0 && ls < a.seqlen) v = Io<T>::ld(xr + (a.perm != nullptr ? a.perm[ls] : ls));
+        xs[i] = v;
     }
-    Io<T>::st(reinterpret_cast<T *>(a.out) + b * a.o_bs + d * a.o_ds + l, a.silu ? silu_f(acc) : acc);
+    float w[kMaxW];
+#pragma unroll
+    for (int i = 0; i < kMaxW; ++i) {
+        const int wi = i - (kMaxW - a.width);
+        w[i] = wi >= 0 ? load_w(a.weight, a.w_dtype, d * a.w_ds + wi * a.w_ws) : 0.f;
+    }
+    const float bias = a.bias != nullptr ? load_w(a.bias, a.w_dtype, d) : 0.f;
+    float ov[kGW];
+#pragma unroll
+    for (int i = 0; i < kGW; ++i) {
+        float acc = bias;
+#pragma unroll
+        for (int k = 0; k < kMaxW; ++k) acc = fmaf(w[k], xs[i + k], acc);
+        ov[i] = a.silu ? silu_t<sizeof(T) == 2>(acc) : acc;
+    }
+    T *orow = reinterpret_cast<T *>(a.out) + b * a.o_bs + d * a.o_ds + l0;
+    if (a.out_vec_ok && l0 + kGW <= a.seqlen) {
+#pragma unroll
+        for (int i = 0; i < kGW; i += Io<T>::kVec) Io<T>::stv(orow + i, reinterpret_cast<const float(&)[Io<T>::kVec]>(ov[i]));
+    } else {
+#pragma unroll
+        for (int i = 0; i < kGW; ++i)
+            if (l0 + i < a.seqlen) Io<T>::st(orow + i, ov[i]);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------- backward
@@ -275,7 +304,7 @@ int run_fwd(const ConvArgs &a, bool vec_ok, cudaStream_t stream) {
             conv_fwd_vec_kernel<T, 1><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(a);
         }
     } else {
-        const int64_t total = (int64_t)a.batch * a.dim * a.seqlen;
+        const int64_t total = (int64_t)a.batch * a.dim * ((a.seqlen + kGW - 1) / kGW);
         conv_fwd_scalar_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(a);
     }
     return check_launch("causal_conv1d_fwd");
@@ -304,6 +333,7 @@ using namespace dimsum;
 extern "C" int dimsum_causal_conv1d_fwd(const dimsum_conv_fwd_params *p, void *stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     DIMSUM_REQUIRE(p != nullptr, DIMSUM_ERR_INVALID, "causal_conv1d_fwd: null params");
+    if (p != nullptr && p->batch == 0) return DIMSUM_OK;   // empty tensors may carry null pointers
     int rc = check_common("causal_conv1d_fwd", p->batch, p->dim, p->seqlen, p->width, p->io_dtype, p->w_dtype);
     if (rc) return rc;
     DIMSUM_REQUIRE(p->x && p->weight && p->out, DIMSUM_ERR_INVALID, "causal_conv1d_fwd: null pointer");
@@ -317,6 +347,7 @@ extern "C" int dimsum_causal_conv1d_fwd(const dimsum_conv_fwd_params *p, void *s
     const int vec = p->io_dtype == DIMSUM_F32 ? 4 : 8;
     const bool vec_ok = p->seqlen % vec == 0 && aligned16(p->x) && aligned16(p->out) && a.x_bs % vec == 0 &&
                         a.x_ds % vec == 0 && a.o_bs % vec == 0 && a.o_ds % vec == 0;
+    a.out_vec_ok = aligned16(p->out) && a.o_bs % 8 == 0 && a.o_ds % 8 == 0;
     switch (p->io_dtype) {
         case DIMSUM_F32: return run_fwd<float>(a, vec_ok, stream);
         case DIMSUM_BF16: return run_fwd<__nv_bfloat16>(a, vec_ok, stream);
@@ -327,6 +358,7 @@ extern "C" int dimsum_causal_conv1d_fwd(const dimsum_conv_fwd_params *p, void *s
 extern "C" int dimsum_causal_conv1d_bwd(const dimsum_conv_bwd_params *p, void *stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     DIMSUM_REQUIRE(p != nullptr, DIMSUM_ERR_INVALID, "causal_conv1d_bwd: null params");
+    if (p != nullptr && p->batch == 0) return DIMSUM_OK;   // empty tensors may carry null pointers
     int rc = check_common("causal_conv1d_bwd", p->batch, p->dim, p->seqlen, p->width, p->io_dtype, p->w_dtype);
     if (rc) return rc;
     DIMSUM_REQUIRE(p->x && p->weight && p->dout && p->dx && p->dweight, DIMSUM_ERR_INVALID, "causal_conv1d_bwd: null pointer");

@@ -145,6 +145,7 @@ __global__ void __launch_bounds__(256) gelu_mul_kernel(const dimsum_gelu_mul_par
 int rowwise_entry(const dimsum_rowwise_params *p, bool gate, void *stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     const char *who = gate ? "gate_residual" : "modulate";
+    if (p != nullptr && p->batch == 0) return DIMSUM_OK;   // empty tensors may carry null pointers
     DIMSUM_REQUIRE(p != nullptr && p->x && p->dst, DIMSUM_ERR_INVALID, "%s: null pointer", who);
     DIMSUM_REQUIRE(gate ? (p->m && p->gate) : (p->shift && p->scale), DIMSUM_ERR_INVALID, "%s: null operand", who);
     DIMSUM_REQUIRE(p->batch >= 0 && p->seqlen > 0 && p->channels > 0, DIMSUM_ERR_INVALID, "%s: bad sizes", who);
@@ -175,6 +176,7 @@ extern "C" int dimsum_gate_residual(const dimsum_rowwise_params *p, void *stream
 
 extern "C" int dimsum_add_rmsnorm(const dimsum_rmsnorm_params *p, void *stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (p != nullptr && p->rows == 0) return DIMSUM_OK;
     DIMSUM_REQUIRE(p != nullptr && p->x && p->weight && p->y, DIMSUM_ERR_INVALID, "add_rmsnorm: null pointer");
     DIMSUM_REQUIRE(p->rows >= 0 && p->channels > 0, DIMSUM_ERR_INVALID, "add_rmsnorm: bad sizes");
     DIMSUM_REQUIRE(p->dtype >= 0 && p->dtype <= 2, DIMSUM_ERR_INVALID, "add_rmsnorm: unknown dtype");
@@ -194,6 +196,7 @@ extern "C" int dimsum_add_rmsnorm(const dimsum_rmsnorm_params *p, void *stream_)
 
 extern "C" int dimsum_gelu_mul(const dimsum_gelu_mul_params *p, void *stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (p != nullptr && p->rows == 0) return DIMSUM_OK;
     DIMSUM_REQUIRE(p != nullptr && p->x && p->y, DIMSUM_ERR_INVALID, "gelu_mul: null pointer");
     DIMSUM_REQUIRE(p->rows >= 0 && p->hidden > 0 && p->dtype >= 0 && p->dtype <= 2, DIMSUM_ERR_INVALID, "gelu_mul: bad arguments");
     const int vec = p->dtype == DIMSUM_F32 ? 4 : 8;

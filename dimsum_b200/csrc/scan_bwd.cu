@@ -399,6 +399,7 @@ using namespace dimsum;
 extern "C" int dimsum_selective_scan_bwd(const dimsum_scan_bwd_params *p, void *stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     DIMSUM_REQUIRE(p != nullptr, DIMSUM_ERR_INVALID, "selective_scan_bwd: null params");
+    if (p != nullptr && p->batch == 0) return DIMSUM_OK;   // empty tensors may carry null pointers
     DIMSUM_REQUIRE(p->batch >= 0 && p->dim > 0 && p->seqlen > 0 && p->dstate > 0, DIMSUM_ERR_INVALID, "selective_scan_bwd: bad sizes");
     DIMSUM_REQUIRE(p->dstate <= 256, DIMSUM_ERR_INVALID, "selective_scan only supports state dimension <= 256");
     DIMSUM_REQUIRE(p->dstate <= 16, DIMSUM_ERR_UNSUPPORTED,

@@ -311,10 +311,12 @@ int launch(const ScanFwdArgs &a, int batch, cudaStream_t stream) {
     constexpr int LC = kRowBytes / (int)sizeof(T);
     auto kern = scan_fwd_kernel<T, kHasZ, kSoftplus, kPoly, kPolyDeg>;
     const int smem = (int)sizeof(ScanSmem<LC>);
-    static bool configured = false;   // per instantiation
-    if (!configured) {
+    static unsigned long long configured = 0;   // per instantiation, one bit per device (the attribute is per device)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!(configured >> (dev & 63) & 1ull)) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        configured = true;
+        configured |= 1ull << (dev & 63);
     }
     const int dpg = a.dim / a.n_groups;
     dim3 grid(a.n_groups * ((dpg + kRows - 1) / kRows), batch);
@@ -358,6 +360,7 @@ using namespace dimsum;
 extern "C" int dimsum_selective_scan_fwd(const dimsum_scan_fwd_params *p, void *stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     DIMSUM_REQUIRE(p != nullptr, DIMSUM_ERR_INVALID, "selective_scan_fwd: null params");
+    if (p != nullptr && p->batch == 0) return DIMSUM_OK;   // empty tensors may carry null pointers
     DIMSUM_REQUIRE(p->batch >= 0 && p->dim > 0 && p->seqlen > 0 && p->dstate > 0, DIMSUM_ERR_INVALID,
                    "selective_scan_fwd: bad sizes batch=%lld dim=%lld seqlen=%lld dstate=%lld", (long long)p->batch,
                    (long long)p->dim, (long long)p->seqlen, (long long)p->dstate);

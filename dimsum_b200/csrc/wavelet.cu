@@ -209,6 +209,7 @@ int run_wavelet(const dimsum_wavelet_params *p, bool inverse, cudaStream_t strea
 int wavelet_entry(const dimsum_wavelet_params *p, bool inverse, void *stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     const char *who = inverse ? "wavelet_packet_inv" : "wavelet_packet_fwd";
+    if (p != nullptr && p->batch == 0) return DIMSUM_OK;   // empty tensors may carry null pointers
     DIMSUM_REQUIRE(p != nullptr && p->src && p->dst, DIMSUM_ERR_INVALID, "%s: null pointer", who);
     DIMSUM_REQUIRE(p->grid > 0 && p->grid % 4 == 0, DIMSUM_ERR_INVALID, "%s: token grid %lld must be a multiple of 4", who,
                    (long long)p->grid);
@@ -237,6 +238,7 @@ extern "C" int dimsum_wavelet_packet_inv(const dimsum_wavelet_params *p, void *s
 
 extern "C" int dimsum_token_gather(const dimsum_gather_params *p, void *stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (p != nullptr && p->batch == 0) return DIMSUM_OK;   // empty tensors may carry null pointers
     DIMSUM_REQUIRE(p != nullptr && p->src && p->dst && p->index, DIMSUM_ERR_INVALID, "token_gather: null pointer");
     DIMSUM_REQUIRE(p->batch >= 0 && p->seqlen > 0 && p->channels > 0, DIMSUM_ERR_INVALID, "token_gather: bad sizes");
     DIMSUM_REQUIRE(p->dtype >= 0 && p->dtype <= 2, DIMSUM_ERR_INVALID, "token_gather: unknown dtype");
