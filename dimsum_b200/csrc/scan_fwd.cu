@@ -13,8 +13,11 @@
 //     its u slot with the gated output, so the epilogue is a pure coalesced 128-bit copy-out;
 //   * the B / C tile is fetched one chunk ahead through registers and parked transposed as [l][n] fp32 (pitch 20), read
 //     as warp-wide 128-bit broadcasts: B and C are fetched once per 128 channels, not once per channel as in the reference;
-//   * kPoly of the 8 state pairs evaluate 2^x as a Cody-Waite polynomial on the FMA pipe instead of MUFU.EX2, because at
-//     16 SFU lanes/clk/SM the exp unit -- not HBM -- is the first limiter of this kernel.
+//   * at 16 SFU lanes/clk/SM the exp unit -- not HBM -- is the first limiter of this kernel (20 MUFU results per element).
+//     When the caller vouches that every row of A is an arithmetic progression, A[d][n] = (n+1) A[d][0] -- true for the
+//     S4D-real initialisation A = -(1..N) of mamba_simple.py:514-521 and checked on the host -- the 16 decays of a step
+//     are the powers r, r^2, .. r^16 of ONE exp (kArith): 1 MUFU + 8 packed multiplies instead of 16 MUFU.  Moving
+//     part of the exps to a polynomial on the FMA pipe was measured and is slower (profiles/r1_scan_fwd_experiments.md).
 #include <type_traits>
 
 #include "common.cuh"
@@ -81,7 +84,7 @@ DEV void store_last_state(const ScanFwdArgs &a, int b, int d, const float2 (&h2)
     }
 }
 
-template <typename T, bool kHasZ, bool kSoftplus, int kPoly, int kPolyDeg>
+template <typename T, bool kHasZ, bool kSoftplus, bool kArith>
 __global__ void __launch_bounds__(kRows, 3) scan_fwd_kernel(const ScanFwdArgs a) {
     constexpr int VEC = Io<T>::kVec;                 // elements per 16 bytes
     constexpr int LC = kRowBytes / (int)sizeof(T);   // steps per chunk: 16 (fp32) / 32 (16-bit)
@@ -226,6 +229,21 @@ __global__ void __launch_bounds__(kRows, 3) scan_fwd_kernel(const ScanFwdArgs a)
             for (int k = 0; k < VEC; ++k) {
                 const float dlt = dv[k];
                 const float du = dlt * uv[k];
+                float2 dec[kNS / 2];
+                if (kArith) {
+                    // A[n] = (n + 1) A[0]: decays are r^(n+1) with r = 2^(delta A2[0])
+                    const float r = ex2_mufu(dlt * A2[0].x);
+                    const float r2 = r * r;
+                    dec[0] = make_float2(r, r2);
+#pragma unroll
+                    for (int p = 1; p < kNS / 2; ++p) dec[p] = mul2(dec[p - 1], splat2(r2));
+                } else {
+#pragma unroll
+                    for (int p = 0; p < kNS / 2; ++p) {
+                        const float2 t = mul2(splat2(dlt), A2[p]);
+                        dec[p] = make_float2(ex2_mufu(t.x), ex2_mufu(t.y));
+                    }
+                }
                 float2 ya = make_float2(0.f, 0.f), yb = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int q = 0; q < kNS / 4; ++q) {
@@ -236,14 +254,7 @@ __global__ void __launch_bounds__(kRows, 3) scan_fwd_kernel(const ScanFwdArgs a)
                         const int p = q * 2 + e;
                         const float2 Bp = e ? make_float2(Bq.z, Bq.w) : make_float2(Bq.x, Bq.y);
                         const float2 Cp = e ? make_float2(Cq.z, Cq.w) : make_float2(Cq.x, Cq.y);
-                        const float2 t = mul2(splat2(dlt), A2[p]);
-                        float2 dec;
-                        if (p < kPoly) {
-                            dec = ex2_poly2<kPolyDeg>(t);
-                        } else {
-                            dec = make_float2(ex2_mufu(t.x), ex2_mufu(t.y));
-                        }
-                        h2[p] = fma2(dec, h2[p], mul2(splat2(du), Bp));
+                        h2[p] = fma2(dec[p], h2[p], mul2(splat2(du), Bp));
                         if (e) yb = fma2(Cp, h2[p], yb); else ya = fma2(Cp, h2[p], ya);
                     }
                 }
@@ -306,10 +317,10 @@ __global__ void __launch_bounds__(kRows, 3) scan_fwd_kernel(const ScanFwdArgs a)
     if (a.x != nullptr && row_ok) store_last_state(a, b, d0 + tid, h2);
 }
 
-template <typename T, bool kHasZ, bool kSoftplus, int kPoly, int kPolyDeg>
+template <typename T, bool kHasZ, bool kSoftplus, bool kArith>
 int launch(const ScanFwdArgs &a, int batch, cudaStream_t stream) {
     constexpr int LC = kRowBytes / (int)sizeof(T);
-    auto kern = scan_fwd_kernel<T, kHasZ, kSoftplus, kPoly, kPolyDeg>;
+    auto kern = scan_fwd_kernel<T, kHasZ, kSoftplus, kArith>;
     const int smem = (int)sizeof(ScanSmem<LC>);
     static unsigned long long configured = 0;   // per instantiation, one bit per device (the attribute is per device)
     int dev = 0;
@@ -324,32 +335,17 @@ int launch(const ScanFwdArgs &a, int batch, cudaStream_t stream) {
     return check_launch("selective_scan_fwd");
 }
 
-template <typename T, int kPoly, int kPolyDeg>
+template <typename T, bool kArith>
 int dispatch2(const ScanFwdArgs &a, int batch, cudaStream_t stream) {
     if (a.z != nullptr) {
-        return a.softplus ? launch<T, true, true, kPoly, kPolyDeg>(a, batch, stream)
-                          : launch<T, true, false, kPoly, kPolyDeg>(a, batch, stream);
+        return a.softplus ? launch<T, true, true, kArith>(a, batch, stream) : launch<T, true, false, kArith>(a, batch, stream);
     }
-    return a.softplus ? launch<T, false, true, kPoly, kPolyDeg>(a, batch, stream)
-                      : launch<T, false, false, kPoly, kPolyDeg>(a, batch, stream);
+    return a.softplus ? launch<T, false, true, kArith>(a, batch, stream) : launch<T, false, false, kArith>(a, batch, stream);
 }
 
-template <typename T, int kPolyDeg>
-int dispatch(const ScanFwdArgs &a, int batch, int poly, cudaStream_t stream) {
-    if (poly == 0) return dispatch2<T, 0, kPolyDeg>(a, batch, stream);
-    if (poly == 2) return dispatch2<T, 2, kPolyDeg>(a, batch, stream);
-    return fail(DIMSUM_ERR_INVALID, "selective_scan_fwd: unsupported poly split %d", poly);
-}
-
-int poly_pairs(int io_dtype) {
-    // developer knob (tools/bench_ops.py sweeps it); default chosen from measurements recorded in profiles/
-    static int env = [] {
-        const char *e = getenv("DIMSUM_SCAN_POLY");
-        return e ? atoi(e) : -1;
-    }();
-    if (env >= 0) return env;
-    (void)io_dtype;
-    return 0;
+template <typename T>
+int dispatch(const ScanFwdArgs &a, int batch, bool arith, cudaStream_t stream) {
+    return arith ? dispatch2<T, true>(a, batch, stream) : dispatch2<T, false>(a, batch, stream);
 }
 
 }  // namespace
@@ -411,10 +407,11 @@ extern "C" int dimsum_selective_scan_fwd(const dimsum_scan_fwd_params *p, void *
     if (p->z) vec_ok = vec_ok && aligned16(p->z) && aligned16(p->out_z) && strides_ok(a.z_bs, a.z_ds) && strides_ok(a.oz_bs, a.oz_ds);
     a.vec_io = vec_ok;
 
-    const int poly = poly_pairs((int)p->io_dtype);
+    // the arithmetic-progression shortcut needs all 16 states (padding states have A = 0, which breaks the progression)
+    const bool arith = p->a_is_arithmetic != 0 && p->dstate == kNS;
     switch (p->io_dtype) {
-        case DIMSUM_F32: return dispatch<float, 5>(a, (int)p->batch, poly, stream);
-        case DIMSUM_BF16: return dispatch<__nv_bfloat16, 3>(a, (int)p->batch, poly, stream);
-        default: return dispatch<__half, 3>(a, (int)p->batch, poly, stream);
+        case DIMSUM_F32: return dispatch<float>(a, (int)p->batch, arith, stream);
+        case DIMSUM_BF16: return dispatch<__nv_bfloat16>(a, (int)p->batch, arith, stream);
+        default: return dispatch<__half>(a, (int)p->batch, arith, stream);
     }
 }

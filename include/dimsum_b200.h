@@ -62,10 +62,14 @@ typedef enum { DIMSUM_F32 = 0, DIMSUM_F16 = 1, DIMSUM_BF16 = 2 } dimsum_dtype;
  * z / out_z               : both NULL or both set; out_z = y * silu(z)
  * perm                    : NULL, or int32[seqlen]: z is read at, and out_z written to, token perm[l]
  *                           (scan-order gather folded into the kernel; inference only)
+ * a_is_arithmetic         : the CALLER asserts that A[d][n] == (n+1) * A[d][0] for every row (the S4D-real
+ *                           initialisation A = -(1..N), mamba_simple.py:514-521); the kernel then derives the 16
+ *                           decays of a step from one exp.  Not checked on the device.  Honoured only for dstate 16.
  */
 typedef struct {
     int64_t batch, dim, seqlen, dstate, n_groups, n_chunks, chunk_len;
     int64_t io_dtype, delta_softplus;
+    int64_t a_is_arithmetic;                 /* see above; 0 = general A */
     int64_t u_batch_stride, u_d_stride;
     int64_t delta_batch_stride, delta_d_stride;
     int64_t z_batch_stride, z_d_stride;

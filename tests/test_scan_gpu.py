@@ -120,3 +120,29 @@ def test_reference_error_behaviour():
     with pytest.raises(NotImplementedError):
         selective_scan_fn(u, u, -torch.rand(4, 32, device="cuda"), torch.randn(1, 32, 16, device="cuda"),
                           torch.randn(1, 32, 16, device="cuda"))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_init_form_A_shortcut_matches_oracle(dtype):
+    """A[d, n] = (n+1) A[d, 0] (S4D-real init): the one-exp-per-step path must meet the same tolerance as the general path."""
+    from dimsum_b200 import selective_scan_cuda
+    from oracle import ref_ops
+    g = torch.Generator().manual_seed(11)
+    R, D, L, N = 2, 192, 1024, 16
+    base = -(0.2 + torch.rand(D, 1, generator=g))
+    A = base * torch.arange(1, N + 1, dtype=torch.float32)
+    assert selective_scan_cuda.rows_are_arithmetic(A.cuda())
+    assert not selective_scan_cuda.rows_are_arithmetic((A + 0.01 * torch.rand(D, N, generator=g)).cuda())
+    u = torch.randn(R, D, L, generator=g).to(dtype)
+    delta = (torch.rand(R, D, L, generator=g) * 0.3).to(dtype)
+    z = torch.randn(R, D, L, generator=g).to(dtype)
+    Bm, Cm = torch.randn(R, 1, N, L, generator=g).to(dtype), torch.randn(R, 1, N, L, generator=g).to(dtype)
+    Dv, bias = torch.randn(D, generator=g), torch.rand(D, generator=g) - 3.0
+    want, last_w = ref_ops.selective_scan_oracle(u, delta, A, Bm, Cm, Dv, z=z, delta_bias=bias, delta_softplus=True,
+                                                 return_last_state=True)
+    out, x, got = selective_scan_cuda.fwd(u.cuda(), delta.cuda(), A.cuda(), Bm.cuda(), Cm.cuda(), Dv.cuda(), z.cuda(), bias.cuda(),
+                                          True, a_arith=True)
+    assert rel_err(got, want) <= tol(dtype), rel_err(got, want)
+    assert rel_err(x[:, :, -1, 1::2], last_w) <= 1e-5
+    _, _, general = selective_scan_cuda.fwd(u.cuda(), delta.cuda(), A.cuda(), Bm.cuda(), Cm.cuda(), Dv.cuda(), z.cuda(), bias.cuda(), True)
+    assert rel_err(got, general) <= tol(dtype)

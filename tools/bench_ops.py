@@ -75,7 +75,12 @@ def main():
                                flush=flush)
             rows.append(dict(op="scan_fwd_infer", dtype=str(dtype), R=R, D=D, L=L, ms=med, ms_best=best, gbs=by / med / 1e6,
                              frac=by / med / 1e6 / pk))
-            by_t = by + s * R * D * L + 4 * R * D * ((L + 31) // 32) * 2 * N
+            A_init = -torch.arange(1, N + 1, device="cuda", dtype=torch.float32).repeat(D, 1)      # S4D-real init form
+            med, best = timeit(lambda: selective_scan_cuda.fwd(u, delta, A_init, Bm, Cm, Dv, z, bias, True, need_out=False,
+                                                               need_x=False, a_arith=True), flush=flush)
+            rows.append(dict(op="scan_fwd_infer_initA", dtype=str(dtype), R=R, D=D, L=L, ms=med, ms_best=best, gbs=by / med / 1e6,
+                             frac=by / med / 1e6 / pk))
+            by_t = by + s * R * D * L + 4 * R * D * ((L + 31) // 32 + 1) * 2 * N
             med, best = timeit(lambda: selective_scan_cuda.fwd(u, delta, A, Bm, Cm, Dv, z, bias, True), flush=flush)
             rows.append(dict(op="scan_fwd_train", dtype=str(dtype), R=R, D=D, L=L, ms=med, ms_best=best, gbs=by_t / med / 1e6,
                              frac=by_t / med / 1e6 / pk))
@@ -105,7 +110,7 @@ def main():
         rows.append(dict(op="wavelet_fwd", dtype=str(dtype), R=512, D=512, L=256, ms=med, ms_best=best, gbs=by_w / med / 1e6,
                          frac=by_w / med / 1e6 / pk))
     for r in rows:
-        print(f"{r['op']:16s} {r['dtype']:15s} R={r['R']:4d} D={r['D']:5d} L={r['L']:5d}  {r['ms']:8.3f} ms (best {r['ms_best']:.3f})"
+        print(f"{r['op']:20s} {r['dtype']:15s} R={r['R']:4d} D={r['D']:5d} L={r['L']:5d}  {r['ms']:8.3f} ms (best {r['ms_best']:.3f})"
               f"  {r['gbs']:8.1f} GB/s  {100 * r['frac']:5.1f}% of measured peak {pk:.0f}")
     if args.json:
         json.dump(rows, open(args.json, "w"), indent=1)
