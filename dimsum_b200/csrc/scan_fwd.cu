@@ -96,7 +96,7 @@ DEV void store_last_state(const ScanFwdArgs &a, int b, int d, const float2 (&h2)
 }
 
 template <typename T, bool kHasZ, bool kSoftplus, bool kArith>
-__global__ void __launch_bounds__(kRows, (kArith && sizeof(T) == 4) ? 4 : 3) scan_fwd_kernel(const ScanFwdArgs a) {
+__global__ void __launch_bounds__(kRows, sizeof(T) == 4 ? 4 : 3) scan_fwd_kernel(const ScanFwdArgs a) {
     constexpr int VEC = Io<T>::kVec;                 // elements per 16 bytes
     constexpr int LC = kRowBytes / (int)sizeof(T);   // steps per chunk: 16 (fp32) / 32 (16-bit)
     constexpr int VPR = kRowBytes / 16;              // 16-byte vectors per tile row = 4
