@@ -278,6 +278,35 @@ def run_b200(args, rank, local_rank, world):
             if hasattr(m, "_arith_key"):
                 m._arith_key = None
 
+    # the same scan launch alone (SM clocks not dragged down by the neighbouring GEMMs' power draw), L2 flushed each time
+    iso_ms = None
+    try:
+        from dimsum_b200 import selective_scan_cuda
+        R_, dt_ = 2 * n, (torch.float32 if args.dtype == "fp32" else torch.bfloat16)
+        gi = torch.Generator(device=dev).manual_seed(5)
+        xz_i = torch.randn(2 * D_INNER, R_, SEQ, generator=gi, device=dev).to(dt_).transpose(0, 1)
+        de_i = (0.5 * torch.rand(D_INNER, R_, SEQ, generator=gi, device=dev)).to(dt_).transpose(0, 1)
+        u_i = torch.randn(R_, D_INNER, SEQ, generator=gi, device=dev).to(dt_)
+        A_i = -0.5 * torch.rand(D_INNER, D_STATE, generator=gi, device=dev) - 0.05
+        B_i = torch.randn(R_, 1, D_STATE, SEQ, generator=gi, device=dev).to(dt_)
+        C_i = torch.randn(R_, 1, D_STATE, SEQ, generator=gi, device=dev).to(dt_)
+        Dv_i, bi_i = torch.ones(D_INNER, device=dev), torch.rand(D_INNER, device=dev) - 3.0
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        run = lambda: selective_scan_cuda.fwd(u_i, de_i, A_i, B_i, C_i, Dv_i, xz_i[:, D_INNER:], bi_i, True, need_out=False, need_x=False)
+        for _ in range(3):
+            run()
+        ts_i = []
+        for _ in range(7):
+            flush.zero_()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(); run(); a1.record()
+            torch.cuda.synchronize()
+            ts_i.append(a0.elapsed_time(a1))
+        iso_ms = sorted(ts_i)[len(ts_i) // 2]
+        del xz_i, de_i, u_i, B_i, C_i, flush
+    except Exception:
+        iso_ms = None
+
     # ------------------------------------------------------------------ end to end: host buffers in, host buffers out
     for i in range(min(2, args.warmup)):
         xd = x_host.to(dev, non_blocking=True)
@@ -342,6 +371,10 @@ def run_b200(args, rank, local_rank, world):
                          "achieved": achieved, "peak": peak, "peak_source": how + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes_per_launch": by,
                          "avg_launch_ms": scan_ms, "launches_timed": n_general,
+                         "isolated": None if iso_ms is None else
+                             {"avg_launch_ms": iso_ms, "frac": by / (iso_ms * 1e-3) / 1e9 / peak,
+                              "note": "identical launch timed alone (general A, L2 flushed): SM clock near max instead of the "
+                                      "power-capped clock it gets between the GEMMs of the step"},
                          "path": "one exp per step (A rows arithmetic, --init-form-fastpath)" if args.init_form_fastpath
                                  else "general A (16 exps per step)",
                          "init_form_A_fastpath": None if fast_ms is None else

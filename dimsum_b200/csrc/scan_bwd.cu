@@ -9,27 +9,34 @@
 //     dB_{l,n} += g_l delta_l u_l  (sum over rows)               dC_{l,n} += dy_l h_l (sum over rows)
 // with dy = dout*silu(z), dz = dout*out*silu'(z), du += D dy, dD += dy u, and the softplus chain rule on ddelta.
 //
-// Mapping: TWO threads per channel row, each owning 8 states as 4 packed f32x2 pairs; a warp = 16 rows, a CTA = 64 rows.
-// The sequence is walked backwards in 16-step chunks restarted from the forward's 16-step checkpoints (x).  Inside a
-// chunk the thread first runs the recurrence forward once, parking the state every 4 steps in shared memory, then
-// handles the four 4-step mini-chunks in reverse: recompute 4 steps (h and a history: 36 packed registers), sweep them
-// backwards.  Per step the two halves of a row meet with two xor-1 shuffles (ddelta, du); the 32 dB / dC partials of a
-// warp's 16 rows are summed through a private padded shared tile (4 STS.128 + 4 LDS.128 + 2 shuffle rounds) and
-// accumulated per CTA, so global memory sees ONE fp32 atomic per (l, n) per 64 rows -- 1/64 of the reference's atomic
-// traffic -- and all of u / delta / dout / z / out / du / ddelta / dz move as coalesced 16-byte vectors.
+// Mapping (third layout of this kernel; the first two put rows on lanes and paid for it in the dB/dC sums):
+//   * a lane owns TWO STATES of a PAIR OF ROWS: every recurrence value is a packed f32x2 (row 2p, row 2p+1), so the
+//     per-row scalars (delta, delta*u, dy) arrive as natural pairs from interleaved shared tiles and only B / C need a
+//     splat -- which the tile stores pre-duplicated;
+//   * 8 lanes (16 states) form a row group that walks its 2 row pairs one after the other, so dB / dC of the 4 rows
+//     accumulate in registers and meet the other 15 groups of the CTA once per 4 steps through shared memory;
+//   * what has to cross lanes per step is only the two 16-state dot products (sum_n e A, sum_n g B): 8 packed values per
+//     lane and 4 steps go through a padded transposing tile, lane j ends up with total j.
+// A CTA owns 64 rows and walks the sequence backwards in 16-step chunks restarted from the forward's 16-step
+// checkpoints (x): one forward sweep parks the state every 4 steps, then the four 4-step mini-chunks are replayed
+// (h and a history in registers) and swept in reverse.  Global memory sees ONE fp32 atomic per (l, n) per 64 rows, and
+// u / delta / dout / z / out / du / ddelta / dz move as coalesced 16-byte vectors.
 #include "common.cuh"
 
 namespace dimsum {
 namespace {
 
-constexpr int kRowsB = 64;                 // rows per CTA
-constexpr int kThreadsB = 2 * kRowsB;      // two threads per row
+constexpr int kT = 128;                    // threads per CTA
+constexpr int kLn = 8;                     // lanes per row group (2 states each)
+constexpr int kGroups = kT / kLn;          // 16 row groups
+constexpr int kPairs = 2 * kGroups;        // 32 row pairs = 64 rows per CTA
+constexpr int kRowsB = 2 * kPairs;
 constexpr int kSub = 16;                   // steps per chunk (== checkpoint spacing of the forward)
 constexpr int kMini = 4;                   // steps whose history lives in registers
-constexpr int kPitch = kSub + 4;           // padded row pitch of the [row][l] tiles (words)
-constexpr int kCkPitch = 4 * 16 + 4;       // [row][4 mini-chunk starts][16 states] (+pad)
-constexpr int kRedPitch = 36;              // [16 rows][32 partials] (+pad)
-constexpr int kHalf = 4;                   // packed pairs per thread (8 states)
+constexpr int kInPitch = kSub + 1;         // float4 units per row pair (odd: conflict-free 16-byte stores in the prep pass)
+constexpr int kDyPitch = kSub + 2;         // float2 units per row pair
+constexpr int kStLane = 20;                // words per lane record of the transposing tile (8 packed values + pad)
+constexpr int kStGroup = kLn * kStLane + 16;   // words per group: odd multiple of 16 -> the two groups of a half warp use disjoint banks
 
 struct ScanBwdArgs {
     const void *u, *delta, *z, *B, *C, *dout, *out;
@@ -39,32 +46,29 @@ struct ScanBwdArgs {
     int64_t u_bs, u_ds, dl_bs, dl_ds, z_bs, z_ds, o_bs, o_ds, g_bs, g_ds;
     int64_t du_bs, du_ds, dd_bs, dd_ds, dz_bs, dz_ds, oz_bs, oz_ds;
     int64_t A_ds, A_ns, B_bs, B_gs, B_ns, C_bs, C_gs, C_ns, dB_bs, dB_gs, dB_ns, dC_bs, dC_gs, dC_ns;
-    int dim, seqlen, dstate, n_groups, n_chunks, softplus, vec_io;
+    int dim, seqlen, dstate, n_groups, n_chunks, softplus, vec_io, vec_bc;
 };
 
 struct BwdSmem {
-    float u[kRowsB][kPitch];
-    float dl[kRowsB][kPitch];
-    float dy[kRowsB][kPitch];
-    float sig[kRowsB][kPitch];               // d softplus / d raw delta
-    float ddl[kRowsB][kPitch];               // outputs
-    float du[kRowsB][kPitch];
-    float Bs[kSub][kPitch];
-    float Cs[kSub][kPitch];
-    float ck[kRowsB][kCkPitch];              // state at the start of each mini-chunk
-    float red[kThreadsB / 32][2][16][kRedPitch];   // per-warp dB/dC reduction tile, double-buffered by step parity
-    float acc[kSub][32 + 1];                 // CTA sums for the chunk: [l][0..15] = dB_n, [l][16..31] = dC_n
+    float4 in[kPairs][kInPitch];          // (delta r0, delta r1, delta*u r0, delta*u r1); later (ddelta r0, r1, du r0, r1)
+    float4 us[kPairs][kInPitch];          // (u r0, u r1, dsoftplus r0, dsoftplus r1)
+    float2 dy[kPairs][kDyPitch];          // (dy r0, dy r1)
+    float4 Bd[kSub][kLn];                 // (B_n0, B_n0, B_n0+1, B_n0+1) per lane
+    float4 Cd[kSub][kLn];
+    float4 hs[kPairs][kSub / kMini - 1][kLn];   // state at the start of mini-chunks 0..2: (n0 r0, n0 r1, n0+1 r0, n0+1 r1)
+    float st[kGroups * kStGroup];         // transposing tile of the row groups; reused for the dB/dC hand-over
+    float2 Dp[kPairs];
 };
 
 template <typename T, bool kHasZ>
-__global__ void __launch_bounds__(kThreadsB, 3) scan_bwd_kernel(const ScanBwdArgs a) {
+__global__ void __launch_bounds__(kT, 4) scan_bwd_kernel(const ScanBwdArgs a) {
     constexpr int VEC = Io<T>::kVec;
+    constexpr int VPR = kSub / VEC;                      // vectors per row chunk
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BwdSmem &s = *reinterpret_cast<BwdSmem *>(smem_raw);
     const int tid = threadIdx.x;
-    const int lane = tid & 31, warp = tid >> 5;
-    const int row = tid >> 1, hf = tid & 1;          // row of the slab, which half of the states
-    const int rw = lane >> 1;                        // row inside the warp (0..15)
+    const int grp = tid >> 3, ln = tid & 7;
+    const int n0 = 2 * ln;                               // first of this lane's two states
     const int b = blockIdx.y;
     const int dpg = a.dim / a.n_groups;
     const int slabs_per_group = (dpg + kRowsB - 1) / kRowsB;
@@ -72,9 +76,6 @@ __global__ void __launch_bounds__(kThreadsB, 3) scan_bwd_kernel(const ScanBwdArg
     const int d0 = g * dpg + (blockIdx.x % slabs_per_group) * kRowsB;
     const int nrows = min(kRowsB, (g + 1) * dpg - d0);
     const int L = a.seqlen;
-    const bool row_ok = row < nrows;
-    const int d = d0 + row;
-    const int n0 = hf * 2 * kHalf;                   // first state of this thread
 
     const T *u = reinterpret_cast<const T *>(a.u) + b * a.u_bs + (int64_t)d0 * a.u_ds;
     const T *dl = reinterpret_cast<const T *>(a.delta) + b * a.dl_bs + (int64_t)d0 * a.dl_ds;
@@ -88,34 +89,44 @@ __global__ void __launch_bounds__(kThreadsB, 3) scan_bwd_kernel(const ScanBwdArg
     const T *Bg = reinterpret_cast<const T *>(a.B) + b * a.B_bs + g * a.B_gs;
     const T *Cg = reinterpret_cast<const T *>(a.C) + b * a.C_bs + g * a.C_gs;
 
-    // per-thread constants: A (log2e-scaled) for this thread's 4 state pairs
-    float2 A2[kHalf];
+    // per-thread constants: A (log2e-scaled) of this lane's 2 states for the 2 x 2 rows of its group
+    float2 A2[2][2];
 #pragma unroll
-    for (int p = 0; p < kHalf; ++p) {
-        const float *Arow = a.A + (int64_t)d * a.A_ds;
-        const int n = n0 + 2 * p;
-        const float a0 = (row_ok && n < a.dstate) ? Arow[n * a.A_ns] : 0.f;
-        const float a1 = (row_ok && n + 1 < a.dstate) ? Arow[(n + 1) * a.A_ns] : 0.f;
-        A2[p] = make_float2(a0 * kLog2e, a1 * kLog2e);
+    for (int q = 0; q < 2; ++q) {
+#pragma unroll
+        for (int si = 0; si < 2; ++si) {
+            const int r = grp * 4 + 2 * q, n = n0 + si;
+            const float a0 = (r < nrows && n < a.dstate) ? a.A[(int64_t)(d0 + r) * a.A_ds + n * a.A_ns] : 0.f;
+            const float a1 = (r + 1 < nrows && n < a.dstate) ? a.A[(int64_t)(d0 + r + 1) * a.A_ds + n * a.A_ns] : 0.f;
+            A2[q][si] = make_float2(a0 * kLog2e, a1 * kLog2e);
+        }
     }
-    const float Dv = (row_ok && a.D != nullptr) ? a.D[d] : 0.f;
-    float2 dA[kHalf], carry[kHalf];            // carry = a_{l+1} g_{l+1} entering the current step from the right
+    if (tid < kPairs) {
+        const int r = 2 * tid;
+        s.Dp[tid] = make_float2((r < nrows && a.D != nullptr) ? a.D[d0 + r] : 0.f,
+                                (r + 1 < nrows && a.D != nullptr) ? a.D[d0 + r + 1] : 0.f);
+    }
+    float2 dA[2][2], carry[2][2];              // carry = a_{l+1} g_{l+1} entering the current step from the right
+    float2 dD_acc[2], dbias_acc[2];            // meaningful on the even lanes (they finish the per-step sums)
 #pragma unroll
-    for (int p = 0; p < kHalf; ++p) { dA[p] = make_float2(0.f, 0.f); carry[p] = make_float2(0.f, 0.f); }
-    float dD_acc = 0.f, dbias_acc = 0.f;
+    for (int q = 0; q < 2; ++q) {
+        dD_acc[q] = dbias_acc[q] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int si = 0; si < 2; ++si) dA[q][si] = carry[q][si] = make_float2(0.f, 0.f);
+    }
+    float *const st_grp = s.st + grp * kStGroup;
 
-    // one forward step of this thread's 8 states; returns the decays
-    auto fwd_step = [&](int i, float2 (&h)[kHalf], float2 (&dec)[kHalf]) {
-        const float dlt = s.dl[row][i];
-        const float du_ = dlt * s.u[row][i];
-        const float4 B0 = *reinterpret_cast<const float4 *>(&s.Bs[i][n0]);
-        const float4 B1 = *reinterpret_cast<const float4 *>(&s.Bs[i][n0 + 4]);
-        const float2 Bp[kHalf] = {make_float2(B0.x, B0.y), make_float2(B0.z, B0.w), make_float2(B1.x, B1.y), make_float2(B1.z, B1.w)};
+    // one forward step of this lane's 2 states x 2 rows; leaves the decays in dec
+    auto fwd_step = [&](int rp, int q, int li, float2 (&h)[2], float2 (&dec)[2]) {
+        const float4 v = s.in[rp][li];
+        const float4 Bv = s.Bd[li][ln];
+        const float2 dlt = make_float2(v.x, v.y), dtu = make_float2(v.z, v.w);
+        const float2 Bs[2] = {make_float2(Bv.x, Bv.y), make_float2(Bv.z, Bv.w)};
 #pragma unroll
-        for (int p = 0; p < kHalf; ++p) {
-            const float2 t = mul2(splat2(dlt), A2[p]);
-            dec[p] = make_float2(ex2_mufu(t.x), ex2_mufu(t.y));
-            h[p] = fma2(dec[p], h[p], mul2(splat2(du_), Bp[p]));
+        for (int si = 0; si < 2; ++si) {
+            const float2 t = mul2(dlt, A2[q][si]);
+            dec[si] = make_float2(ex2_mufu(t.x), ex2_mufu(t.y));
+            h[si] = fma2(dec[si], h[si], mul2(dtu, Bs[si]));
         }
     };
 
@@ -123,21 +134,24 @@ __global__ void __launch_bounds__(kThreadsB, 3) scan_bwd_kernel(const ScanBwdArg
     for (int k = n_sub - 1; k >= 0; --k) {
         const int l0 = k * kSub;
         // ------------------------------------------------------------ (a) coalesced loads + elementwise prep
-        {
-            constexpr int VPR = kSub / VEC;                      // vectors per row chunk
-            for (int idx = tid; idx < kRowsB * VPR; idx += kThreadsB) {
-                const int r = idx / VPR, v = idx % VPR;
-                const int col = v * VEC, l = l0 + col;
-                float uv[VEC], dv[VEC], gv[VEC], sg[VEC];
+        // item = (row pair, 16-byte vector of steps); two neighbouring lanes take the two halves of a 32-byte sector and
+        // a quarter warp covers four row pairs, which with the odd tile pitch makes the 16-byte tile stores conflict-free
+        for (int idx = tid; idx < kPairs * VPR; idx += kT) {
+            const int rp = (idx >> 1) % kPairs;
+            const int col = ((idx & 1) + 2 * (idx / (2 * kPairs))) * VEC, l = l0 + col;
+            float uv[2][VEC], dv[2][VEC], gv[2][VEC], sg[2][VEC];
 #pragma unroll
-                for (int i = 0; i < VEC; ++i) { uv[i] = 0.f; dv[i] = 0.f; gv[i] = 0.f; sg[i] = 0.f; }
+            for (int c = 0; c < 2; ++c) {
+                const int r = 2 * rp + c;
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) { uv[c][i] = 0.f; dv[c][i] = 0.f; gv[c][i] = 0.f; sg[c][i] = 0.f; }
                 if (r < nrows && l < L) {
                     const bool full = a.vec_io && l + VEC <= L;
                     float zv[VEC], ov[VEC], raw[VEC];
                     if (full) {
-                        Io<T>::ldv(u + (int64_t)r * a.u_ds + l, uv);
+                        Io<T>::ldv(u + (int64_t)r * a.u_ds + l, uv[c]);
                         Io<T>::ldv(dl + (int64_t)r * a.dl_ds + l, raw);
-                        Io<T>::ldv(go + (int64_t)r * a.g_ds + l, gv);
+                        Io<T>::ldv(go + (int64_t)r * a.g_ds + l, gv[c]);
                         if (kHasZ) {
                             Io<T>::ldv(zz + (int64_t)r * a.z_ds + l, zv);
                             Io<T>::ldv(oo + (int64_t)r * a.o_ds + l, ov);
@@ -146,9 +160,9 @@ __global__ void __launch_bounds__(kThreadsB, 3) scan_bwd_kernel(const ScanBwdArg
 #pragma unroll
                         for (int i = 0; i < VEC; ++i) {
                             const bool ok = l + i < L;
-                            uv[i] = ok ? Io<T>::ld(u + (int64_t)r * a.u_ds + l + i) : 0.f;
+                            uv[c][i] = ok ? Io<T>::ld(u + (int64_t)r * a.u_ds + l + i) : 0.f;
                             raw[i] = ok ? Io<T>::ld(dl + (int64_t)r * a.dl_ds + l + i) : 0.f;
-                            gv[i] = ok ? Io<T>::ld(go + (int64_t)r * a.g_ds + l + i) : 0.f;
+                            gv[c][i] = ok ? Io<T>::ld(go + (int64_t)r * a.g_ds + l + i) : 0.f;
                             if (kHasZ) {
                                 zv[i] = ok ? Io<T>::ld(zz + (int64_t)r * a.z_ds + l + i) : 0.f;
                                 ov[i] = ok ? Io<T>::ld(oo + (int64_t)r * a.o_ds + l + i) : 0.f;
@@ -161,20 +175,20 @@ __global__ void __launch_bounds__(kThreadsB, 3) scan_bwd_kernel(const ScanBwdArg
                     for (int i = 0; i < VEC; ++i) {
                         const float x = raw[i] + bias;
                         if (a.softplus) {
-                            dv[i] = softplus_f(x);
-                            sg[i] = x <= 20.f ? sigmoid_f(x) : 1.f;
+                            dv[c][i] = softplus_f(x);
+                            sg[c][i] = x <= 20.f ? sigmoid_f(x) : 1.f;
                         } else {
-                            dv[i] = x;
-                            sg[i] = 1.f;
+                            dv[c][i] = x;
+                            sg[c][i] = 1.f;
                         }
                         if (kHasZ) {
                             const float sz = sigmoid_f(zv[i]);
                             const float silu = zv[i] * sz;
-                            dzv[i] = gv[i] * ov[i] * sz * fmaf(zv[i], 1.f - sz, 1.f);   // d/dz [z sigmoid(z)]
+                            dzv[i] = gv[c][i] * ov[i] * sz * fmaf(zv[i], 1.f - sz, 1.f);   // d/dz [z sigmoid(z)]
                             ozv[i] = ov[i] * silu;
-                            gv[i] *= silu;
+                            gv[c][i] *= silu;
                         }
-                        if (l + i >= L) { dv[i] = 0.f; uv[i] = 0.f; gv[i] = 0.f; sg[i] = 0.f; }
+                        if (l + i >= L) { dv[c][i] = 0.f; uv[c][i] = 0.f; gv[c][i] = 0.f; sg[c][i] = 0.f; }
                     }
                     if (kHasZ) {
                         if (full) {
@@ -191,172 +205,198 @@ __global__ void __launch_bounds__(kThreadsB, 3) scan_bwd_kernel(const ScanBwdArg
                         }
                     }
                 }
+            }
 #pragma unroll
-                for (int i = 0; i < VEC; i += 4) {
-                    *reinterpret_cast<float4 *>(&s.u[r][col + i]) = make_float4(uv[i], uv[i + 1], uv[i + 2], uv[i + 3]);
-                    *reinterpret_cast<float4 *>(&s.dl[r][col + i]) = make_float4(dv[i], dv[i + 1], dv[i + 2], dv[i + 3]);
-                    *reinterpret_cast<float4 *>(&s.dy[r][col + i]) = make_float4(gv[i], gv[i + 1], gv[i + 2], gv[i + 3]);
-                    *reinterpret_cast<float4 *>(&s.sig[r][col + i]) = make_float4(sg[i], sg[i + 1], sg[i + 2], sg[i + 3]);
+            for (int i = 0; i < VEC; ++i) {
+                s.in[rp][col + i] = make_float4(dv[0][i], dv[1][i], dv[0][i] * uv[0][i], dv[1][i] * uv[1][i]);
+                s.us[rp][col + i] = make_float4(uv[0][i], uv[1][i], sg[0][i], sg[1][i]);
+            }
+#pragma unroll
+            for (int i = 0; i < VEC; i += 2)
+                *reinterpret_cast<float4 *>(&s.dy[rp][col + i]) = make_float4(gv[0][i], gv[1][i], gv[0][i + 1], gv[1][i + 1]);
+        }
+        // B / C tiles, duplicated so that a lane's 16-byte load is two ready-made splats
+        for (int idx = tid; idx < 2 * 16 * VPR; idx += kT) {
+            const int which = idx / (16 * VPR), rem = idx % (16 * VPR);
+            const int n = rem % 16, col = (rem / 16) * VEC;
+            const T *src = (which ? Cg + n * a.C_ns : Bg + n * a.B_ns) + l0 + col;
+            float bv[VEC];
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) bv[i] = 0.f;
+            if (n < a.dstate && l0 + col < L) {
+                if (a.vec_bc && l0 + col + VEC <= L) {
+                    Io<T>::ldv(src, bv);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) bv[i] = (l0 + col + i < L) ? Io<T>::ld(src + i) : 0.f;
                 }
             }
-            for (int idx = tid; idx < kSub * 16; idx += kThreadsB) {     // B / C tile [l][n]
-                const int l = idx % kSub, n = idx / kSub;
-                const bool ok = n < a.dstate && l0 + l < L;
-                s.Bs[l][n] = ok ? Io<T>::ld(Bg + n * a.B_ns + l0 + l) : 0.f;
-                s.Cs[l][n] = ok ? Io<T>::ld(Cg + n * a.C_ns + l0 + l) : 0.f;
-            }
-            for (int idx = tid; idx < kSub * 32; idx += kThreadsB) s.acc[idx / 32][idx % 32] = 0.f;
+            float4 *tile = which ? &s.Cd[0][0] : &s.Bd[0][0];
+#pragma unroll
+            for (int i = 0; i < VEC; ++i)
+                reinterpret_cast<float2 *>(tile + (col + i) * kLn)[n] = make_float2(bv[i], bv[i]);
         }
         __syncthreads();
 
-        // ------------------------------------------------------------ (b) one forward pass: mini-chunk start states
-        float2 hist[kMini + 1][kHalf], dec[kMini][kHalf];
+        // ------------------------------------------------------------ (b) one forward sweep: mini-chunk start states
+        float2 h3[2][2];                                        // state at the start of the last mini-chunk
 #pragma unroll
-        for (int p = 0; p < kHalf; ++p) hist[0][p] = make_float2(0.f, 0.f);
-        if (k > 0 && row_ok) {                                  // state after l0 steps: planar checkpoint record
-            const int ck = (l0 - 1) / 32, half = (l0 % 32 == 16) ? 0 : 1;
-            const float *xp = a.x + (((int64_t)b * a.dim + d) * a.n_chunks + ck) * (2 * a.dstate) + half * a.dstate;
+        for (int q = 0; q < 2; ++q) {
+            const int rp = grp * 2 + q;
+            float2 h[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, dtmp[2];
+            if (k > 0) {                                        // state after l0 steps: planar checkpoint record
+                const int ck = (l0 - 1) / 32, half = (l0 % 32 == 16) ? 0 : 1;
+                const int r = 2 * rp;
+                const float *xp = a.x + (((int64_t)b * a.dim + d0 + r) * a.n_chunks + ck) * (2 * a.dstate) + half * a.dstate;
+                const int64_t next = (int64_t)a.n_chunks * 2 * a.dstate;
 #pragma unroll
-            for (int p = 0; p < kHalf; ++p) {
-                const int n = n0 + 2 * p;
-                if (n < a.dstate) hist[0][p].x = xp[n];
-                if (n + 1 < a.dstate) hist[0][p].y = xp[n + 1];
+                for (int si = 0; si < 2; ++si) {
+                    const int n = n0 + si;
+                    if (n < a.dstate) {
+                        if (r < nrows) h[si].x = xp[n];
+                        if (r + 1 < nrows) h[si].y = xp[next + n];
+                    }
+                }
             }
-        }
-        {
-            float2 h[kHalf], dtmp[kHalf];
 #pragma unroll
-            for (int p = 0; p < kHalf; ++p) h[p] = hist[0][p];
+            for (int m = 0; m < kSub / kMini - 1; ++m) {
+                s.hs[rp][m][ln] = make_float4(h[0].x, h[0].y, h[1].x, h[1].y);
 #pragma unroll
-            for (int m = 0; m < kSub / kMini - 1; ++m) {          // mini-chunks 0..2: only their end state is kept
-                float *ckp = &s.ck[row][m * 16 + n0];
-                *reinterpret_cast<float4 *>(ckp) = make_float4(h[0].x, h[0].y, h[1].x, h[1].y);
-                *reinterpret_cast<float4 *>(ckp + 4) = make_float4(h[2].x, h[2].y, h[3].x, h[3].y);
-#pragma unroll
-                for (int i = 0; i < kMini; ++i) fwd_step(m * kMini + i, h, dtmp);
+                for (int i = 0; i < kMini; ++i) fwd_step(rp, q, m * kMini + i, h, dtmp);
             }
-            float *ckp = &s.ck[row][3 * 16 + n0];
-            *reinterpret_cast<float4 *>(ckp) = make_float4(h[0].x, h[0].y, h[1].x, h[1].y);
-            *reinterpret_cast<float4 *>(ckp + 4) = make_float4(h[2].x, h[2].y, h[3].x, h[3].y);
+            h3[q][0] = h[0];
+            h3[q][1] = h[1];
         }
 
         // ------------------------------------------------------------ (c) mini-chunks in reverse
 #pragma unroll 1
         for (int m = kSub / kMini - 1; m >= 0; --m) {
-            {   // recompute the 4 steps, keeping h and a
-                const float *ckp = &s.ck[row][m * 16 + n0];
-                const float4 c0 = *reinterpret_cast<const float4 *>(ckp), c1 = *reinterpret_cast<const float4 *>(ckp + 4);
-                hist[0][0] = make_float2(c0.x, c0.y); hist[0][1] = make_float2(c0.z, c0.w);
-                hist[0][2] = make_float2(c1.x, c1.y); hist[0][3] = make_float2(c1.z, c1.w);
+            float2 accB[kMini][2], accC[kMini][2];              // dB / dC of this group's rows (packed: even row, odd row)
 #pragma unroll
-                for (int i = 0; i < kMini; ++i) {
-#pragma unroll
-                    for (int p = 0; p < kHalf; ++p) hist[i + 1][p] = hist[i][p];
-                    fwd_step(m * kMini + i, hist[i + 1], dec[i]);
-                }
+            for (int i = 0; i < kMini; ++i) {
+                accB[i][0] = accB[i][1] = make_float2(0.f, 0.f);
+                accC[i][0] = accC[i][1] = make_float2(0.f, 0.f);
             }
 #pragma unroll
-            for (int i = kMini - 1; i >= 0; --i) {
-                const int li = m * kMini + i;
-                const float dlt = s.dl[row][li], uv = s.u[row][li], dyv = s.dy[row][li];
-                const float4 B0 = *reinterpret_cast<const float4 *>(&s.Bs[li][n0]);
-                const float4 B1 = *reinterpret_cast<const float4 *>(&s.Bs[li][n0 + 4]);
-                const float4 C0 = *reinterpret_cast<const float4 *>(&s.Cs[li][n0]);
-                const float4 C1 = *reinterpret_cast<const float4 *>(&s.Cs[li][n0 + 4]);
-                const float2 Bp[kHalf] = {make_float2(B0.x, B0.y), make_float2(B0.z, B0.w), make_float2(B1.x, B1.y), make_float2(B1.z, B1.w)};
-                const float2 Cp[kHalf] = {make_float2(C0.x, C0.y), make_float2(C0.z, C0.w), make_float2(C1.x, C1.y), make_float2(C1.z, C1.w)};
-                float2 accE = make_float2(0.f, 0.f), accG = make_float2(0.f, 0.f);
-                float2 dBp[kHalf], dCp[kHalf];
-                const float du_ = dlt * uv;
-#pragma unroll
-                for (int p = 0; p < kHalf; ++p) {
-                    const float2 gl = fma2(Cp[p], splat2(dyv), carry[p]);
-                    carry[p] = mul2(dec[i][p], gl);
-                    const float2 e = mul2(carry[p], hist[i][p]);            // g a h_{l-1}
-                    dA[p] = fma2(e, splat2(dlt), dA[p]);
-                    accE = fma2(e, A2[p], accE);
-                    accG = fma2(gl, Bp[p], accG);
-                    dBp[p] = mul2(gl, splat2(du_));
-                    dCp[p] = mul2(hist[i + 1][p], splat2(dyv));
-                }
-                // the two halves of the row meet: ddelta = sum_n e A + u sum_n g B ; du = delta sum_n g B + D dy
-                float E = (accE.x + accE.y) * kLn2, G = accG.x + accG.y;     // A = A2 * ln 2
-                E += __shfl_xor_sync(0xffffffffu, E, 1);
-                G += __shfl_xor_sync(0xffffffffu, G, 1);
-                if (hf == 0) {
-                    const float ddraw = fmaf(uv, G, E) * s.sig[row][li];
-                    s.ddl[row][li] = ddraw;
-                    dbias_acc += ddraw;
-                    dD_acc = fmaf(dyv, uv, dD_acc);
+            for (int q = 0; q < 2; ++q) {
+                const int rp = grp * 2 + q;
+                float2 hist[kMini + 1][2], dec[kMini][2];
+                if (m == kSub / kMini - 1) {
+                    hist[0][0] = h3[q][0];
+                    hist[0][1] = h3[q][1];
                 } else {
-                    s.du[row][li] = fmaf(dlt, G, Dv * dyv);
+                    const float4 c = s.hs[rp][m][ln];
+                    hist[0][0] = make_float2(c.x, c.y);
+                    hist[0][1] = make_float2(c.z, c.w);
                 }
-                // dB / dC of the warp's 16 rows: private tile (double-buffered by step parity, so one __syncwarp per step
-                // and the read-back latency overlaps the next step's arithmetic), column sums, two shuffle rounds, CTA sums
-                float(*red)[kRedPitch] = s.red[warp][li & 1];
-                float *rp = &red[rw][n0];
-                *reinterpret_cast<float4 *>(rp) = make_float4(dBp[0].x, dBp[0].y, dBp[1].x, dBp[1].y);
-                *reinterpret_cast<float4 *>(rp + 4) = make_float4(dBp[2].x, dBp[2].y, dBp[3].x, dBp[3].y);
-                *reinterpret_cast<float4 *>(rp + 16) = make_float4(dCp[0].x, dCp[0].y, dCp[1].x, dCp[1].y);
-                *reinterpret_cast<float4 *>(rp + 20) = make_float4(dCp[2].x, dCp[2].y, dCp[3].x, dCp[3].y);
-                __syncwarp();
-                {
-                    const int rg = lane >> 3, cg = lane & 7;                 // rows 4 rg .. 4 rg + 3, columns 4 cg .. 4 cg + 3
-                    const float4 w0 = *reinterpret_cast<const float4 *>(&red[4 * rg][4 * cg]);
-                    const float4 w1 = *reinterpret_cast<const float4 *>(&red[4 * rg + 1][4 * cg]);
-                    const float4 w2 = *reinterpret_cast<const float4 *>(&red[4 * rg + 2][4 * cg]);
-                    const float4 w3 = *reinterpret_cast<const float4 *>(&red[4 * rg + 3][4 * cg]);
-                    float4 v = make_float4((w0.x + w1.x) + (w2.x + w3.x), (w0.y + w1.y) + (w2.y + w3.y),
-                                           (w0.z + w1.z) + (w2.z + w3.z), (w0.w + w1.w) + (w2.w + w3.w));
 #pragma unroll
-                    for (int o = 8; o <= 16; o <<= 1) {
-                        v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
-                        v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
-                        v.z += __shfl_xor_sync(0xffffffffu, v.z, o);
-                        v.w += __shfl_xor_sync(0xffffffffu, v.w, o);
+                for (int i = 0; i < kMini; ++i) {               // replay the 4 steps, keeping h and a
+                    hist[i + 1][0] = hist[i][0];
+                    hist[i + 1][1] = hist[i][1];
+                    fwd_step(rp, q, m * kMini + i, hist[i + 1], dec[i]);
+                }
+#pragma unroll
+                for (int i = kMini - 1; i >= 0; --i) {
+                    const int li = m * kMini + i;
+                    const float4 v = s.in[rp][li];
+                    const float2 dyv = s.dy[rp][li];
+                    const float4 Bv = s.Bd[li][ln], Cv = s.Cd[li][ln];
+                    const float2 dlt = make_float2(v.x, v.y), dtu = make_float2(v.z, v.w);
+                    const float2 Bs[2] = {make_float2(Bv.x, Bv.y), make_float2(Bv.z, Bv.w)};
+                    const float2 Cs[2] = {make_float2(Cv.x, Cv.y), make_float2(Cv.z, Cv.w)};
+                    float2 P = make_float2(0.f, 0.f), Q = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int si = 0; si < 2; ++si) {
+                        const float2 gl = fma2(Cs[si], dyv, carry[q][si]);
+                        carry[q][si] = mul2(dec[i][si], gl);
+                        const float2 e = mul2(carry[q][si], hist[i][si]);     // g a h_{l-1}
+                        dA[q][si] = fma2(e, dlt, dA[q][si]);
+                        P = fma2(e, A2[q][si], P);
+                        Q = fma2(gl, Bs[si], Q);
+                        accB[i][si] = fma2(gl, dtu, accB[i][si]);
+                        accC[i][si] = fma2(hist[i + 1][si], dyv, accC[i][si]);
                     }
-                    if (rg == 0) {
-                        atomicAdd(&s.acc[li][4 * cg], v.x);
-                        atomicAdd(&s.acc[li][4 * cg + 1], v.y);
-                        atomicAdd(&s.acc[li][4 * cg + 2], v.z);
-                        atomicAdd(&s.acc[li][4 * cg + 3], v.w);
-                    }
+                    *reinterpret_cast<float4 *>(st_grp + ln * kStLane + 4 * i) = make_float4(P.x, P.y, Q.x, Q.y);
+                }
+                __syncwarp();
+                // transpose: lane j = 2 i + w collects sum_n of value w (0: e A, 1: g B) of step i, both rows
+                float2 tot = *reinterpret_cast<const float2 *>(st_grp + 2 * ln);
+#pragma unroll
+                for (int o = 1; o < kLn; ++o) tot = add2(tot, *reinterpret_cast<const float2 *>(st_grp + o * kStLane + 2 * ln));
+                const float qx = __shfl_down_sync(0xffffffffu, tot.x, 1), qy = __shfl_down_sync(0xffffffffu, tot.y, 1);
+                if ((ln & 1) == 0) {
+                    // ddelta = (sum_n e A + u sum_n g B) softplus' ; du = delta sum_n g B + D dy     (A = A2 * ln 2)
+                    const int li = m * kMini + (ln >> 1);
+                    const float4 v = s.in[rp][li], w = s.us[rp][li];
+                    const float2 dyv = s.dy[rp][li], Dv = s.Dp[rp];
+                    const float dd0 = fmaf(w.x, qx, tot.x * kLn2) * w.z, dd1 = fmaf(w.y, qy, tot.y * kLn2) * w.w;
+                    const float du0 = fmaf(v.x, qx, Dv.x * dyv.x), du1 = fmaf(v.y, qy, Dv.y * dyv.y);
+                    s.in[rp][li] = make_float4(dd0, dd1, du0, du1);
+                    dbias_acc[q].x += dd0;
+                    dbias_acc[q].y += dd1;
+                    dD_acc[q].x = fmaf(dyv.x, w.x, dD_acc[q].x);
+                    dD_acc[q].y = fmaf(dyv.y, w.y, dD_acc[q].y);
+                }
+                __syncwarp();
+            }
+            // dB / dC of the 4 steps: each group leaves its 64 sums in its own tile, 128 threads add the 16 groups
+            // (thread = (B|C, state, step), steps fastest so that 4 lanes hit 16 contiguous bytes), one atomic each
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int si = c & 1;
+                float4 f;
+                if (c < 2) f = make_float4(accB[0][si].x + accB[0][si].y, accB[1][si].x + accB[1][si].y,
+                                           accB[2][si].x + accB[2][si].y, accB[3][si].x + accB[3][si].y);
+                else       f = make_float4(accC[0][si].x + accC[0][si].y, accC[1][si].x + accC[1][si].y,
+                                           accC[2][si].x + accC[2][si].y, accC[3][si].x + accC[3][si].y);
+                *reinterpret_cast<float4 *>(st_grp + (c * kLn + ln) * 4) = f;
+            }
+            __syncthreads();
+            {
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+                for (int gg = 0; gg < kGroups; gg += 4) {
+                    s0 += s.st[gg * kStGroup + tid];
+                    s1 += s.st[(gg + 1) * kStGroup + tid];
+                    s2 += s.st[(gg + 2) * kStGroup + tid];
+                    s3 += s.st[(gg + 3) * kStGroup + tid];
+                }
+                const int c = tid >> 5, n = 2 * ((tid >> 2) & 7) + (c & 1), l = l0 + m * kMini + (tid & 3);
+                if (n < a.dstate && l < L) {
+                    float *dst = c < 2 ? a.dB + b * a.dB_bs + g * a.dB_gs + n * a.dB_ns + l
+                                       : a.dC + b * a.dC_bs + g * a.dC_gs + n * a.dC_ns + l;
+                    atomicAdd(dst, (s0 + s1) + (s2 + s3));
                 }
             }
+            __syncthreads();
         }
-        __syncthreads();
 
-        // ------------------------------------------------------------ (d) coalesced stores + dB/dC flush
-        {
-            constexpr int VPR = kSub / VEC;
-            for (int idx = tid; idx < kRowsB * VPR; idx += kThreadsB) {
-                const int r = idx / VPR, v = idx % VPR;
-                const int col = v * VEC, l = l0 + col;
-                if (r < nrows && l < L) {
-                    float dd[VEC], du_[VEC];
+        // ------------------------------------------------------------ (d) coalesced stores of ddelta / du
+        for (int idx = tid; idx < kPairs * VPR; idx += kT) {
+            const int rp = (idx >> 1) % kPairs;
+            const int col = ((idx & 1) + 2 * (idx / (2 * kPairs))) * VEC, l = l0 + col;
+            float dd[2][VEC], du_[2][VEC];
 #pragma unroll
-                    for (int i = 0; i < VEC; ++i) { dd[i] = s.ddl[r][col + i]; du_[i] = s.du[r][col + i]; }
+            for (int i = 0; i < VEC; ++i) {
+                const float4 o = s.in[rp][col + i];
+                dd[0][i] = o.x; dd[1][i] = o.y; du_[0][i] = o.z; du_[1][i] = o.w;
+            }
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int r = 2 * rp + c;
+                if (r < nrows && l < L) {
                     if (a.vec_io && l + VEC <= L) {
-                        Io<T>::stv(ddp + (int64_t)r * a.dd_ds + l, dd);
-                        Io<T>::stv(dup + (int64_t)r * a.du_ds + l, du_);
+                        Io<T>::stv(ddp + (int64_t)r * a.dd_ds + l, dd[c]);
+                        Io<T>::stv(dup + (int64_t)r * a.du_ds + l, du_[c]);
                     } else {
 #pragma unroll
                         for (int i = 0; i < VEC; ++i) {
                             if (l + i < L) {
-                                Io<T>::st(ddp + (int64_t)r * a.dd_ds + l + i, dd[i]);
-                                Io<T>::st(dup + (int64_t)r * a.du_ds + l + i, du_[i]);
+                                Io<T>::st(ddp + (int64_t)r * a.dd_ds + l + i, dd[c][i]);
+                                Io<T>::st(dup + (int64_t)r * a.du_ds + l + i, du_[c][i]);
                             }
                         }
                     }
-                }
-            }
-            for (int idx = tid; idx < kSub * 32; idx += kThreadsB) {
-                const int l = idx % kSub, v = idx / kSub;          // l fastest: consecutive lanes hit consecutive addresses
-                const int n = v & 15;
-                if (n < a.dstate && l0 + l < L) {
-                    float *dst = v < 16 ? a.dB + b * a.dB_bs + g * a.dB_gs + n * a.dB_ns + l0 + l
-                                        : a.dC + b * a.dC_bs + g * a.dC_gs + n * a.dC_ns + l0 + l;
-                    atomicAdd(dst, s.acc[l][v]);
                 }
             }
         }
@@ -364,16 +404,35 @@ __global__ void __launch_bounds__(kThreadsB, 3) scan_bwd_kernel(const ScanBwdArg
     }
 
     // ------------------------------------------------------------ per-row parameter gradients
-    if (row_ok) {
 #pragma unroll
-        for (int p = 0; p < kHalf; ++p) {
-            const int n = n0 + 2 * p;
-            if (n < a.dstate) atomicAdd(a.dA + (int64_t)d * a.dstate + n, dA[p].x);
-            if (n + 1 < a.dstate) atomicAdd(a.dA + (int64_t)d * a.dstate + n + 1, dA[p].y);
+    for (int q = 0; q < 2; ++q) {
+        const int r = grp * 4 + 2 * q;
+#pragma unroll
+        for (int si = 0; si < 2; ++si) {
+            const int n = n0 + si;
+            if (n < a.dstate) {
+                if (r < nrows) atomicAdd(a.dA + (int64_t)(d0 + r) * a.dstate + n, dA[q][si].x);
+                if (r + 1 < nrows) atomicAdd(a.dA + (int64_t)(d0 + r + 1) * a.dstate + n, dA[q][si].y);
+            }
         }
-        if (hf == 0) {
-            if (a.dD != nullptr) atomicAdd(a.dD + d, dD_acc);
-            if (a.ddelta_bias != nullptr) atomicAdd(a.ddelta_bias + d, dbias_acc);
+        // the four even lanes each saw one step of every mini-chunk
+        float2 dd = dD_acc[q], db = dbias_acc[q];
+#pragma unroll
+        for (int o = 2; o <= 4; o <<= 1) {
+            dd.x += __shfl_xor_sync(0xffffffffu, dd.x, o);
+            dd.y += __shfl_xor_sync(0xffffffffu, dd.y, o);
+            db.x += __shfl_xor_sync(0xffffffffu, db.x, o);
+            db.y += __shfl_xor_sync(0xffffffffu, db.y, o);
+        }
+        if (ln == 0) {
+            if (r < nrows) {
+                if (a.dD != nullptr) atomicAdd(a.dD + d0 + r, dd.x);
+                if (a.ddelta_bias != nullptr) atomicAdd(a.ddelta_bias + d0 + r, db.x);
+            }
+            if (r + 1 < nrows) {
+                if (a.dD != nullptr) atomicAdd(a.dD + d0 + r + 1, dd.y);
+                if (a.ddelta_bias != nullptr) atomicAdd(a.ddelta_bias + d0 + r + 1, db.y);
+            }
         }
     }
 }
@@ -385,7 +444,7 @@ int run(const ScanBwdArgs &a, int batch, cudaStream_t stream) {
     const int smem = (int)sizeof(BwdSmem);
     auto go = [&](auto kern) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        kern<<<grid, kThreadsB, smem, stream>>>(a);
+        kern<<<grid, kT, smem, stream>>>(a);
     };
     if (a.z != nullptr) go(scan_bwd_kernel<T, true>); else go(scan_bwd_kernel<T, false>);
     return check_launch("selective_scan_bwd");
@@ -440,6 +499,8 @@ extern "C" int dimsum_selective_scan_bwd(const dimsum_scan_bwd_params *p, void *
     a.vec_io = ok(p->u, a.u_bs, a.u_ds) && ok(p->delta, a.dl_bs, a.dl_ds) && ok(p->dout, a.g_bs, a.g_ds) &&
                ok(p->z, a.z_bs, a.z_ds) && ok(p->out, a.o_bs, a.o_ds) && ok(p->dz, a.dz_bs, a.dz_ds) &&
                ok(p->out_z_recompute, a.oz_bs, a.oz_ds) && ok(p->du, a.du_bs, a.du_ds) && ok(p->ddelta, a.dd_bs, a.dd_ds);
+    a.vec_bc = aligned16(p->B) && aligned16(p->C) && a.B_bs % vec == 0 && a.B_gs % vec == 0 && a.B_ns % vec == 0 &&
+               a.C_bs % vec == 0 && a.C_gs % vec == 0 && a.C_ns % vec == 0;
     switch (p->io_dtype) {
         case DIMSUM_F32: return run<float>(a, (int)p->batch, stream);
         case DIMSUM_BF16: return run<__nv_bfloat16>(a, (int)p->batch, stream);
