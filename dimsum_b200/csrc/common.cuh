@@ -164,6 +164,9 @@ struct Io<float> {
     static DEV void stv(float *p, const float (&v)[4]) {
         *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
     }
+    // four consecutive elements (16 bytes here, 8 bytes for the 16-bit types)
+    static DEV void ld4(const float *p, float (&v)[4]) { ldv(p, v); }
+    static DEV void st4(float *p, const float (&v)[4]) { stv(p, v); }
 };
 
 template <>
@@ -189,6 +192,15 @@ struct Io<__nv_bfloat16> {
             w[i] = reinterpret_cast<uint32_t &>(h);
         }
         *reinterpret_cast<uint4 *>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    static DEV void ld4(const __nv_bfloat16 *p, float (&v)[4]) {
+        const uint2 r = *reinterpret_cast<const uint2 *>(p);
+        v[0] = __uint_as_float(r.x << 16); v[1] = __uint_as_float(r.x & 0xffff0000u);
+        v[2] = __uint_as_float(r.y << 16); v[3] = __uint_as_float(r.y & 0xffff0000u);
+    }
+    static DEV void st4(__nv_bfloat16 *p, const float (&v)[4]) {
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+        *reinterpret_cast<uint2 *>(p) = make_uint2(reinterpret_cast<uint32_t &>(h0), reinterpret_cast<uint32_t &>(h1));
     }
 };
 
@@ -216,6 +228,15 @@ struct Io<__half> {
             w[i] = reinterpret_cast<uint32_t &>(h);
         }
         *reinterpret_cast<uint4 *>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    static DEV void ld4(const __half *p, float (&v)[4]) {
+        const uint2 r = *reinterpret_cast<const uint2 *>(p);
+        const float2 f0 = __half22float2(reinterpret_cast<const __half2 &>(r.x)), f1 = __half22float2(reinterpret_cast<const __half2 &>(r.y));
+        v[0] = f0.x; v[1] = f0.y; v[2] = f1.x; v[3] = f1.y;
+    }
+    static DEV void st4(__half *p, const float (&v)[4]) {
+        __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+        *reinterpret_cast<uint2 *>(p) = make_uint2(reinterpret_cast<uint32_t &>(h0), reinterpret_cast<uint32_t &>(h1));
     }
 };
 

@@ -33,8 +33,14 @@ constexpr int kPairs = 2 * kGroups;        // 32 row pairs = 64 rows per CTA
 constexpr int kRowsB = 2 * kPairs;
 constexpr int kSub = 16;                   // steps per chunk (== checkpoint spacing of the forward)
 constexpr int kMini = 4;                   // steps whose history lives in registers
-constexpr int kInPitch = kSub + 1;         // float4 units per row pair (odd: conflict-free 16-byte stores in the prep pass)
-constexpr int kDyPitch = kSub + 2;         // float2 units per row pair
+constexpr int kMinis = kSub / kMini;
+constexpr int kTileG = 2 * kMini + 1;      // float4 units per row group inside a slab (2 row pairs x 4 steps + 1: neighbouring
+                                           // groups start 4 banks apart, so their 8-byte broadcast loads do not collide)
+constexpr int kTileM = kGroups * kTileG + 1;   // float4 units per mini-chunk slab of a [mini][row pair][step] tile; slab
+                                           // stride = 1 mod 8 makes the 16-byte stores of the prep pass conflict-free
+// element (mini m, row pair p, step i) of a row-pair tile
+__device__ __forceinline__ constexpr int tile_at(int m, int p, int i) { return m * kTileM + (p >> 1) * kTileG + (p & 1) * kMini + i; }
+constexpr int kMinCtas = 3;                 // CTAs per SM the register budget is cut for (168 registers; 128 spills)
 constexpr int kStLane = 20;                // words per lane record of the transposing tile (8 packed values + pad)
 constexpr int kStGroup = kLn * kStLane + 16;   // words per group: odd multiple of 16 -> the two groups of a half warp use disjoint banks
 
@@ -50,20 +56,20 @@ struct ScanBwdArgs {
 };
 
 struct BwdSmem {
-    float4 in[kPairs][kInPitch];          // (delta r0, delta r1, delta*u r0, delta*u r1); later (ddelta r0, r1, du r0, r1)
-    float4 us[kPairs][kInPitch];          // (u r0, u r1, dsoftplus r0, dsoftplus r1)
-    float2 dy[kPairs][kDyPitch];          // (dy r0, dy r1)
+    // row-pair tiles, element (mini m, row pair p, step i) at [tile_at(m, p, i)]
+    float4 X[kMinis * kTileM];            // (delta r0, delta r1, delta*u r0, delta*u r1); later (ddelta r0, r1, du r0, r1)
+    float4 Y[kMinis * kTileM];            // (dy r0, dy r1, D dy r0, D dy r1)
+    float4 Z[kMinis * kTileM];            // (ln2 s' r0, ln2 s' r1, u s' r0, u s' r1) with s' = d softplus / d raw delta
     float4 Bd[kSub][kLn];                 // (B_n0, B_n0, B_n0+1, B_n0+1) per lane
     float4 Cd[kSub][kLn];
     float4 hs[kPairs][kSub / kMini - 1][kLn];   // state at the start of mini-chunks 0..2: (n0 r0, n0 r1, n0+1 r0, n0+1 r1)
     float st[kGroups * kStGroup];         // transposing tile of the row groups; reused for the dB/dC hand-over
-    float2 Dp[kPairs];
 };
 
 template <typename T, bool kHasZ>
-__global__ void __launch_bounds__(kT, 4) scan_bwd_kernel(const ScanBwdArgs a) {
-    constexpr int VEC = Io<T>::kVec;
-    constexpr int VPR = kSub / VEC;                      // vectors per row chunk
+__global__ void __launch_bounds__(kT, kMinCtas) scan_bwd_kernel(const ScanBwdArgs a) {
+    constexpr int VEC = kMini;                           // global I/O in 4-element vectors (16 bytes fp32, 8 bytes bf16/fp16)
+    constexpr int VPR = kSub / VEC;                      // vectors per row chunk: the 128 threads are 32 row pairs x 4 vectors
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BwdSmem &s = *reinterpret_cast<BwdSmem *>(smem_raw);
     const int tid = threadIdx.x;
@@ -101,25 +107,32 @@ __global__ void __launch_bounds__(kT, 4) scan_bwd_kernel(const ScanBwdArgs a) {
             A2[q][si] = make_float2(a0 * kLog2e, a1 * kLog2e);
         }
     }
-    if (tid < kPairs) {
-        const int r = 2 * tid;
-        s.Dp[tid] = make_float2((r < nrows && a.D != nullptr) ? a.D[d0 + r] : 0.f,
-                                (r + 1 < nrows && a.D != nullptr) ? a.D[d0 + r + 1] : 0.f);
-    }
     float2 dA[2][2], carry[2][2];              // carry = a_{l+1} g_{l+1} entering the current step from the right
-    float2 dD_acc[2], dbias_acc[2];            // meaningful on the even lanes (they finish the per-step sums)
+    float2 dbias_acc[2];                       // meaningful on the even lanes (they finish the per-step sums)
+    float dD_prep[2] = {0.f, 0.f};             // sum_l dy u of the two rows this thread loads in the prep pass
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
-        dD_acc[q] = dbias_acc[q] = make_float2(0.f, 0.f);
+        dbias_acc[q] = make_float2(0.f, 0.f);
 #pragma unroll
         for (int si = 0; si < 2; ++si) dA[q][si] = carry[q][si] = make_float2(0.f, 0.f);
     }
     float *const st_grp = s.st + grp * kStGroup;
+    // prep / store item of this thread: (row pair, 16-byte vector of steps), vectors fastest -> VPR neighbouring lanes
+    // cover one row's 64-byte chunk
+    const bool io_thread = tid < kPairs * VPR;
+    const int io_rp = tid / VPR, io_col = (tid % VPR) * VEC;
+    float Dio[2] = {0.f, 0.f}, bias_io[2] = {0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        const int r = 2 * io_rp + c;
+        if (io_thread && r < nrows) {
+            if (a.D != nullptr) Dio[c] = a.D[d0 + r];
+            if (a.delta_bias != nullptr) bias_io[c] = a.delta_bias[d0 + r];
+        }
+    }
 
     // one forward step of this lane's 2 states x 2 rows; leaves the decays in dec
-    auto fwd_step = [&](int rp, int q, int li, float2 (&h)[2], float2 (&dec)[2]) {
-        const float4 v = s.in[rp][li];
-        const float4 Bv = s.Bd[li][ln];
+    auto fwd_step = [&](const float4 v, const float4 Bv, int q, float2 (&h)[2], float2 (&dec)[2]) {
         const float2 dlt = make_float2(v.x, v.y), dtu = make_float2(v.z, v.w);
         const float2 Bs[2] = {make_float2(Bv.x, Bv.y), make_float2(Bv.z, Bv.w)};
 #pragma unroll
@@ -134,33 +147,30 @@ __global__ void __launch_bounds__(kT, 4) scan_bwd_kernel(const ScanBwdArgs a) {
     for (int k = n_sub - 1; k >= 0; --k) {
         const int l0 = k * kSub;
         // ------------------------------------------------------------ (a) coalesced loads + elementwise prep
-        // item = (row pair, 16-byte vector of steps); two neighbouring lanes take the two halves of a 32-byte sector and
-        // a quarter warp covers four row pairs, which with the odd tile pitch makes the 16-byte tile stores conflict-free
-        for (int idx = tid; idx < kPairs * VPR; idx += kT) {
-            const int rp = (idx >> 1) % kPairs;
-            const int col = ((idx & 1) + 2 * (idx / (2 * kPairs))) * VEC, l = l0 + col;
-            float uv[2][VEC], dv[2][VEC], gv[2][VEC], sg[2][VEC];
+        if (io_thread) {
+            const int rp = io_rp, col = io_col, l = l0 + col;
+            float dv[2][VEC], tu[2][VEC], gv[2][VEC], dg[2][VEC], sk[2][VEC], su[2][VEC];
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
                 const int r = 2 * rp + c;
 #pragma unroll
-                for (int i = 0; i < VEC; ++i) { uv[c][i] = 0.f; dv[c][i] = 0.f; gv[c][i] = 0.f; sg[c][i] = 0.f; }
+                for (int i = 0; i < VEC; ++i) { dv[c][i] = tu[c][i] = gv[c][i] = dg[c][i] = sk[c][i] = su[c][i] = 0.f; }
                 if (r < nrows && l < L) {
                     const bool full = a.vec_io && l + VEC <= L;
-                    float zv[VEC], ov[VEC], raw[VEC];
+                    float uv[VEC], zv[VEC], ov[VEC], raw[VEC];
                     if (full) {
-                        Io<T>::ldv(u + (int64_t)r * a.u_ds + l, uv[c]);
-                        Io<T>::ldv(dl + (int64_t)r * a.dl_ds + l, raw);
-                        Io<T>::ldv(go + (int64_t)r * a.g_ds + l, gv[c]);
+                        Io<T>::ld4(u + (int64_t)r * a.u_ds + l, uv);
+                        Io<T>::ld4(dl + (int64_t)r * a.dl_ds + l, raw);
+                        Io<T>::ld4(go + (int64_t)r * a.g_ds + l, gv[c]);
                         if (kHasZ) {
-                            Io<T>::ldv(zz + (int64_t)r * a.z_ds + l, zv);
-                            Io<T>::ldv(oo + (int64_t)r * a.o_ds + l, ov);
+                            Io<T>::ld4(zz + (int64_t)r * a.z_ds + l, zv);
+                            Io<T>::ld4(oo + (int64_t)r * a.o_ds + l, ov);
                         }
                     } else {
 #pragma unroll
                         for (int i = 0; i < VEC; ++i) {
                             const bool ok = l + i < L;
-                            uv[c][i] = ok ? Io<T>::ld(u + (int64_t)r * a.u_ds + l + i) : 0.f;
+                            uv[i] = ok ? Io<T>::ld(u + (int64_t)r * a.u_ds + l + i) : 0.f;
                             raw[i] = ok ? Io<T>::ld(dl + (int64_t)r * a.dl_ds + l + i) : 0.f;
                             gv[c][i] = ok ? Io<T>::ld(go + (int64_t)r * a.g_ds + l + i) : 0.f;
                             if (kHasZ) {
@@ -169,17 +179,16 @@ __global__ void __launch_bounds__(kT, 4) scan_bwd_kernel(const ScanBwdArgs a) {
                             }
                         }
                     }
-                    const float bias = a.delta_bias != nullptr ? a.delta_bias[d0 + r] : 0.f;
                     float dzv[VEC], ozv[VEC];
 #pragma unroll
                     for (int i = 0; i < VEC; ++i) {
-                        const float x = raw[i] + bias;
+                        const float x = raw[i] + bias_io[c];
+                        float sgm = 1.f;
                         if (a.softplus) {
                             dv[c][i] = softplus_f(x);
-                            sg[c][i] = x <= 20.f ? sigmoid_f(x) : 1.f;
+                            sgm = x <= 20.f ? sigmoid_f(x) : 1.f;
                         } else {
                             dv[c][i] = x;
-                            sg[c][i] = 1.f;
                         }
                         if (kHasZ) {
                             const float sz = sigmoid_f(zv[i]);
@@ -188,12 +197,17 @@ __global__ void __launch_bounds__(kT, 4) scan_bwd_kernel(const ScanBwdArgs a) {
                             ozv[i] = ov[i] * silu;
                             gv[c][i] *= silu;
                         }
-                        if (l + i >= L) { dv[c][i] = 0.f; uv[c][i] = 0.f; gv[c][i] = 0.f; sg[c][i] = 0.f; }
+                        if (l + i >= L) { dv[c][i] = 0.f; uv[i] = 0.f; gv[c][i] = 0.f; sgm = 0.f; }
+                        tu[c][i] = dv[c][i] * uv[i];
+                        dg[c][i] = Dio[c] * gv[c][i];
+                        sk[c][i] = kLn2 * sgm;
+                        su[c][i] = uv[i] * sgm;
+                        dD_prep[c] = fmaf(gv[c][i], uv[i], dD_prep[c]);
                     }
                     if (kHasZ) {
                         if (full) {
-                            Io<T>::stv(dzp + (int64_t)r * a.dz_ds + l, dzv);
-                            if (ozp != nullptr) Io<T>::stv(ozp + (int64_t)r * a.oz_ds + l, ozv);
+                            Io<T>::st4(dzp + (int64_t)r * a.dz_ds + l, dzv);
+                            if (ozp != nullptr) Io<T>::st4(ozp + (int64_t)r * a.oz_ds + l, ozv);
                         } else {
 #pragma unroll
                             for (int i = 0; i < VEC; ++i) {
@@ -208,12 +222,11 @@ __global__ void __launch_bounds__(kT, 4) scan_bwd_kernel(const ScanBwdArgs a) {
             }
 #pragma unroll
             for (int i = 0; i < VEC; ++i) {
-                s.in[rp][col + i] = make_float4(dv[0][i], dv[1][i], dv[0][i] * uv[0][i], dv[1][i] * uv[1][i]);
-                s.us[rp][col + i] = make_float4(uv[0][i], uv[1][i], sg[0][i], sg[1][i]);
+                const int e = tile_at(col / kMini + i / kMini, rp, i % kMini);
+                s.X[e] = make_float4(dv[0][i], dv[1][i], tu[0][i], tu[1][i]);
+                s.Y[e] = make_float4(gv[0][i], gv[1][i], dg[0][i], dg[1][i]);
+                s.Z[e] = make_float4(sk[0][i], sk[1][i], su[0][i], su[1][i]);
             }
-#pragma unroll
-            for (int i = 0; i < VEC; i += 2)
-                *reinterpret_cast<float4 *>(&s.dy[rp][col + i]) = make_float4(gv[0][i], gv[1][i], gv[0][i + 1], gv[1][i + 1]);
         }
         // B / C tiles, duplicated so that a lane's 16-byte load is two ready-made splats
         for (int idx = tid; idx < 2 * 16 * VPR; idx += kT) {
@@ -225,7 +238,7 @@ __global__ void __launch_bounds__(kT, 4) scan_bwd_kernel(const ScanBwdArgs a) {
             for (int i = 0; i < VEC; ++i) bv[i] = 0.f;
             if (n < a.dstate && l0 + col < L) {
                 if (a.vec_bc && l0 + col + VEC <= L) {
-                    Io<T>::ldv(src, bv);
+                    Io<T>::ld4(src, bv);
                 } else {
 #pragma unroll
                     for (int i = 0; i < VEC; ++i) bv[i] = (l0 + col + i < L) ? Io<T>::ld(src + i) : 0.f;
@@ -240,52 +253,62 @@ __global__ void __launch_bounds__(kT, 4) scan_bwd_kernel(const ScanBwdArgs a) {
 
         // ------------------------------------------------------------ (b) one forward sweep: mini-chunk start states
         float2 h3[2][2];                                        // state at the start of the last mini-chunk
+        {
+            float2 h[2][2], dtmp[2];
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            const int rp = grp * 2 + q;
-            float2 h[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, dtmp[2];
-            if (k > 0) {                                        // state after l0 steps: planar checkpoint record
-                const int ck = (l0 - 1) / 32, half = (l0 % 32 == 16) ? 0 : 1;
-                const int r = 2 * rp;
-                const float *xp = a.x + (((int64_t)b * a.dim + d0 + r) * a.n_chunks + ck) * (2 * a.dstate) + half * a.dstate;
-                const int64_t next = (int64_t)a.n_chunks * 2 * a.dstate;
+            for (int q = 0; q < 2; ++q) {
+                h[q][0] = h[q][1] = make_float2(0.f, 0.f);
+                if (k > 0) {                                    // state after l0 steps: planar checkpoint record
+                    const int ck = (l0 - 1) / 32, half = (l0 % 32 == 16) ? 0 : 1;
+                    const int r = grp * 4 + 2 * q;
+                    const float *xp = a.x + (((int64_t)b * a.dim + d0 + r) * a.n_chunks + ck) * (2 * a.dstate) + half * a.dstate;
+                    const int64_t next = (int64_t)a.n_chunks * 2 * a.dstate;
 #pragma unroll
-                for (int si = 0; si < 2; ++si) {
-                    const int n = n0 + si;
-                    if (n < a.dstate) {
-                        if (r < nrows) h[si].x = xp[n];
-                        if (r + 1 < nrows) h[si].y = xp[next + n];
+                    for (int si = 0; si < 2; ++si) {
+                        const int n = n0 + si;
+                        if (n < a.dstate) {
+                            if (r < nrows) h[q][si].x = xp[n];
+                            if (r + 1 < nrows) h[q][si].y = xp[next + n];
+                        }
                     }
                 }
             }
 #pragma unroll
-            for (int m = 0; m < kSub / kMini - 1; ++m) {
-                s.hs[rp][m][ln] = make_float4(h[0].x, h[0].y, h[1].x, h[1].y);
+            for (int m = 0; m < kMinis - 1; ++m) {
 #pragma unroll
-                for (int i = 0; i < kMini; ++i) fwd_step(rp, q, m * kMini + i, h, dtmp);
+                for (int q = 0; q < 2; ++q) s.hs[grp * 2 + q][m][ln] = make_float4(h[q][0].x, h[q][0].y, h[q][1].x, h[q][1].y);
+#pragma unroll
+                for (int i = 0; i < kMini; ++i) {
+                    const float4 Bv = s.Bd[m * kMini + i][ln];           // one load serves both row pairs
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) fwd_step(s.X[tile_at(m, grp * 2 + q, i)], Bv, q, h[q], dtmp);
+                }
             }
-            h3[q][0] = h[0];
-            h3[q][1] = h[1];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) { h3[q][0] = h[q][0]; h3[q][1] = h[q][1]; }
         }
 
         // ------------------------------------------------------------ (c) mini-chunks in reverse
 #pragma unroll 1
-        for (int m = kSub / kMini - 1; m >= 0; --m) {
-            float2 accB[kMini][2], accC[kMini][2];              // dB / dC of this group's rows (packed: even row, odd row)
+        for (int m = kMinis - 1; m >= 0; --m) {
+            float accB[kMini][2], accC[kMini][2];               // dB / dC of this group's 4 rows
+            float4 Bm[kMini], Cm[kMini];                        // B / C of the 4 steps: loaded once, used by both row pairs
 #pragma unroll
             for (int i = 0; i < kMini; ++i) {
-                accB[i][0] = accB[i][1] = make_float2(0.f, 0.f);
-                accC[i][0] = accC[i][1] = make_float2(0.f, 0.f);
+                accB[i][0] = accB[i][1] = accC[i][0] = accC[i][1] = 0.f;
+                Bm[i] = s.Bd[m * kMini + i][ln];
+                Cm[i] = s.Cd[m * kMini + i][ln];
             }
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
-                const int rp = grp * 2 + q;
+                const int e0 = tile_at(m, grp * 2 + q, 0);
                 float2 hist[kMini + 1][2], dec[kMini][2];
-                if (m == kSub / kMini - 1) {
+                float4 xv[kMini];
+                if (m == kMinis - 1) {
                     hist[0][0] = h3[q][0];
                     hist[0][1] = h3[q][1];
                 } else {
-                    const float4 c = s.hs[rp][m][ln];
+                    const float4 c = s.hs[grp * 2 + q][m][ln];
                     hist[0][0] = make_float2(c.x, c.y);
                     hist[0][1] = make_float2(c.z, c.w);
                 }
@@ -293,17 +316,15 @@ __global__ void __launch_bounds__(kT, 4) scan_bwd_kernel(const ScanBwdArgs a) {
                 for (int i = 0; i < kMini; ++i) {               // replay the 4 steps, keeping h and a
                     hist[i + 1][0] = hist[i][0];
                     hist[i + 1][1] = hist[i][1];
-                    fwd_step(rp, q, m * kMini + i, hist[i + 1], dec[i]);
+                    xv[i] = s.X[e0 + i];
+                    fwd_step(xv[i], Bm[i], q, hist[i + 1], dec[i]);
                 }
 #pragma unroll
                 for (int i = kMini - 1; i >= 0; --i) {
-                    const int li = m * kMini + i;
-                    const float4 v = s.in[rp][li];
-                    const float2 dyv = s.dy[rp][li];
-                    const float4 Bv = s.Bd[li][ln], Cv = s.Cd[li][ln];
-                    const float2 dlt = make_float2(v.x, v.y), dtu = make_float2(v.z, v.w);
-                    const float2 Bs[2] = {make_float2(Bv.x, Bv.y), make_float2(Bv.z, Bv.w)};
-                    const float2 Cs[2] = {make_float2(Cv.x, Cv.y), make_float2(Cv.z, Cv.w)};
+                    const float2 dyv = *reinterpret_cast<const float2 *>(&s.Y[e0 + i]);
+                    const float2 dlt = make_float2(xv[i].x, xv[i].y), dtu = make_float2(xv[i].z, xv[i].w);
+                    const float2 Bs[2] = {make_float2(Bm[i].x, Bm[i].y), make_float2(Bm[i].z, Bm[i].w)};
+                    const float2 Cs[2] = {make_float2(Cm[i].x, Cm[i].y), make_float2(Cm[i].z, Cm[i].w)};
                     float2 P = make_float2(0.f, 0.f), Q = make_float2(0.f, 0.f);
 #pragma unroll
                     for (int si = 0; si < 2; ++si) {
@@ -313,8 +334,8 @@ __global__ void __launch_bounds__(kT, 4) scan_bwd_kernel(const ScanBwdArgs a) {
                         dA[q][si] = fma2(e, dlt, dA[q][si]);
                         P = fma2(e, A2[q][si], P);
                         Q = fma2(gl, Bs[si], Q);
-                        accB[i][si] = fma2(gl, dtu, accB[i][si]);
-                        accC[i][si] = fma2(hist[i + 1][si], dyv, accC[i][si]);
+                        accB[i][si] = fmaf(gl.y, dtu.y, fmaf(gl.x, dtu.x, accB[i][si]));
+                        accC[i][si] = fmaf(hist[i + 1][si].y, dyv.y, fmaf(hist[i + 1][si].x, dyv.x, accC[i][si]));
                     }
                     *reinterpret_cast<float4 *>(st_grp + ln * kStLane + 4 * i) = make_float4(P.x, P.y, Q.x, Q.y);
                 }
@@ -325,17 +346,13 @@ __global__ void __launch_bounds__(kT, 4) scan_bwd_kernel(const ScanBwdArgs a) {
                 for (int o = 1; o < kLn; ++o) tot = add2(tot, *reinterpret_cast<const float2 *>(st_grp + o * kStLane + 2 * ln));
                 const float qx = __shfl_down_sync(0xffffffffu, tot.x, 1), qy = __shfl_down_sync(0xffffffffu, tot.y, 1);
                 if ((ln & 1) == 0) {
-                    // ddelta = (sum_n e A + u sum_n g B) softplus' ; du = delta sum_n g B + D dy     (A = A2 * ln 2)
-                    const int li = m * kMini + (ln >> 1);
-                    const float4 v = s.in[rp][li], w = s.us[rp][li];
-                    const float2 dyv = s.dy[rp][li], Dv = s.Dp[rp];
-                    const float dd0 = fmaf(w.x, qx, tot.x * kLn2) * w.z, dd1 = fmaf(w.y, qy, tot.y * kLn2) * w.w;
-                    const float du0 = fmaf(v.x, qx, Dv.x * dyv.x), du1 = fmaf(v.y, qy, Dv.y * dyv.y);
-                    s.in[rp][li] = make_float4(dd0, dd1, du0, du1);
+                    // ddelta = (ln2 sum_n e A2 + u sum_n g B) s' ; du = delta sum_n g B + D dy
+                    const int e = e0 + (ln >> 1);
+                    const float4 xr = s.X[e], yr = s.Y[e], zr = s.Z[e];
+                    const float dd0 = fmaf(zr.z, qx, tot.x * zr.x), dd1 = fmaf(zr.w, qy, tot.y * zr.y);
+                    s.X[e] = make_float4(dd0, dd1, fmaf(xr.x, qx, yr.z), fmaf(xr.y, qy, yr.w));
                     dbias_acc[q].x += dd0;
                     dbias_acc[q].y += dd1;
-                    dD_acc[q].x = fmaf(dyv.x, w.x, dD_acc[q].x);
-                    dD_acc[q].y = fmaf(dyv.y, w.y, dD_acc[q].y);
                 }
                 __syncwarp();
             }
@@ -344,11 +361,8 @@ __global__ void __launch_bounds__(kT, 4) scan_bwd_kernel(const ScanBwdArgs a) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 const int si = c & 1;
-                float4 f;
-                if (c < 2) f = make_float4(accB[0][si].x + accB[0][si].y, accB[1][si].x + accB[1][si].y,
-                                           accB[2][si].x + accB[2][si].y, accB[3][si].x + accB[3][si].y);
-                else       f = make_float4(accC[0][si].x + accC[0][si].y, accC[1][si].x + accC[1][si].y,
-                                           accC[2][si].x + accC[2][si].y, accC[3][si].x + accC[3][si].y);
+                const float4 f = c < 2 ? make_float4(accB[0][si], accB[1][si], accB[2][si], accB[3][si])
+                                       : make_float4(accC[0][si], accC[1][si], accC[2][si], accC[3][si]);
                 *reinterpret_cast<float4 *>(st_grp + (c * kLn + ln) * 4) = f;
             }
             __syncthreads();
@@ -372,13 +386,12 @@ __global__ void __launch_bounds__(kT, 4) scan_bwd_kernel(const ScanBwdArgs a) {
         }
 
         // ------------------------------------------------------------ (d) coalesced stores of ddelta / du
-        for (int idx = tid; idx < kPairs * VPR; idx += kT) {
-            const int rp = (idx >> 1) % kPairs;
-            const int col = ((idx & 1) + 2 * (idx / (2 * kPairs))) * VEC, l = l0 + col;
+        if (io_thread) {
+            const int rp = io_rp, col = io_col, l = l0 + col;
             float dd[2][VEC], du_[2][VEC];
 #pragma unroll
             for (int i = 0; i < VEC; ++i) {
-                const float4 o = s.in[rp][col + i];
+                const float4 o = s.X[tile_at(col / kMini + i / kMini, rp, i % kMini)];
                 dd[0][i] = o.x; dd[1][i] = o.y; du_[0][i] = o.z; du_[1][i] = o.w;
             }
 #pragma unroll
@@ -386,8 +399,8 @@ __global__ void __launch_bounds__(kT, 4) scan_bwd_kernel(const ScanBwdArgs a) {
                 const int r = 2 * rp + c;
                 if (r < nrows && l < L) {
                     if (a.vec_io && l + VEC <= L) {
-                        Io<T>::stv(ddp + (int64_t)r * a.dd_ds + l, dd[c]);
-                        Io<T>::stv(dup + (int64_t)r * a.du_ds + l, du_[c]);
+                        Io<T>::st4(ddp + (int64_t)r * a.dd_ds + l, dd[c]);
+                        Io<T>::st4(dup + (int64_t)r * a.du_ds + l, du_[c]);
                     } else {
 #pragma unroll
                         for (int i = 0; i < VEC; ++i) {
@@ -415,24 +428,27 @@ __global__ void __launch_bounds__(kT, 4) scan_bwd_kernel(const ScanBwdArgs a) {
                 if (r + 1 < nrows) atomicAdd(a.dA + (int64_t)(d0 + r + 1) * a.dstate + n, dA[q][si].y);
             }
         }
-        // the four even lanes each saw one step of every mini-chunk
-        float2 dd = dD_acc[q], db = dbias_acc[q];
+        if (a.ddelta_bias != nullptr) {                   // the four even lanes each saw one step of every mini-chunk
+            float2 db = dbias_acc[q];
 #pragma unroll
-        for (int o = 2; o <= 4; o <<= 1) {
-            dd.x += __shfl_xor_sync(0xffffffffu, dd.x, o);
-            dd.y += __shfl_xor_sync(0xffffffffu, dd.y, o);
-            db.x += __shfl_xor_sync(0xffffffffu, db.x, o);
-            db.y += __shfl_xor_sync(0xffffffffu, db.y, o);
+            for (int o = 2; o <= 4; o <<= 1) {
+                db.x += __shfl_xor_sync(0xffffffffu, db.x, o);
+                db.y += __shfl_xor_sync(0xffffffffu, db.y, o);
+            }
+            if (ln == 0) {
+                if (r < nrows) atomicAdd(a.ddelta_bias + d0 + r, db.x);
+                if (r + 1 < nrows) atomicAdd(a.ddelta_bias + d0 + r + 1, db.y);
+            }
         }
-        if (ln == 0) {
-            if (r < nrows) {
-                if (a.dD != nullptr) atomicAdd(a.dD + d0 + r, dd.x);
-                if (a.ddelta_bias != nullptr) atomicAdd(a.ddelta_bias + d0 + r, db.x);
-            }
-            if (r + 1 < nrows) {
-                if (a.dD != nullptr) atomicAdd(a.dD + d0 + r + 1, dd.y);
-                if (a.ddelta_bias != nullptr) atomicAdd(a.ddelta_bias + d0 + r + 1, db.y);
-            }
+    }
+    if (a.dD != nullptr && tid < kPairs * VPR) {          // warp-uniform: whole warps take part in the shuffles
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            float v = dD_prep[c];
+#pragma unroll
+            for (int o = 1; o < VPR; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            const int r = 2 * io_rp + c;
+            if (tid % VPR == 0 && r < nrows) atomicAdd(a.dD + d0 + r, v);
         }
     }
 }
@@ -494,12 +510,14 @@ extern "C" int dimsum_selective_scan_bwd(const dimsum_scan_bwd_params *p, void *
     a.dim = (int)p->dim; a.seqlen = (int)p->seqlen; a.dstate = (int)p->dstate; a.n_groups = (int)p->n_groups;
     a.n_chunks = (int)p->n_chunks; a.softplus = p->delta_softplus != 0;
 
-    const int vec = p->io_dtype == DIMSUM_F32 ? 4 : 8;
-    auto ok = [&](const void *ptr, int64_t bs, int64_t ds) { return ptr == nullptr || (aligned16(ptr) && bs % vec == 0 && ds % vec == 0); };
+    const int vec = 4;                                    // elements per vector access; 16 bytes fp32, 8 bytes for 16-bit types
+    const uintptr_t amask = p->io_dtype == DIMSUM_F32 ? 15u : 7u;
+    auto al = [&](const void *ptr) { return (reinterpret_cast<uintptr_t>(ptr) & amask) == 0; };
+    auto ok = [&](const void *ptr, int64_t bs, int64_t ds) { return ptr == nullptr || (al(ptr) && bs % vec == 0 && ds % vec == 0); };
     a.vec_io = ok(p->u, a.u_bs, a.u_ds) && ok(p->delta, a.dl_bs, a.dl_ds) && ok(p->dout, a.g_bs, a.g_ds) &&
                ok(p->z, a.z_bs, a.z_ds) && ok(p->out, a.o_bs, a.o_ds) && ok(p->dz, a.dz_bs, a.dz_ds) &&
                ok(p->out_z_recompute, a.oz_bs, a.oz_ds) && ok(p->du, a.du_bs, a.du_ds) && ok(p->ddelta, a.dd_bs, a.dd_ds);
-    a.vec_bc = aligned16(p->B) && aligned16(p->C) && a.B_bs % vec == 0 && a.B_gs % vec == 0 && a.B_ns % vec == 0 &&
+    a.vec_bc = al(p->B) && al(p->C) && a.B_bs % vec == 0 && a.B_gs % vec == 0 && a.B_ns % vec == 0 &&
                a.C_bs % vec == 0 && a.C_gs % vec == 0 && a.C_ns % vec == 0;
     switch (p->io_dtype) {
         case DIMSUM_F32: return run<float>(a, (int)p->batch, stream);
