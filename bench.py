@@ -278,9 +278,11 @@ def run_b200(args, rank, local_rank, world):
             if hasattr(m, "_arith_key"):
                 m._arith_key = None
 
-    # the same scan launch alone (SM clocks not dragged down by the neighbouring GEMMs' power draw), L2 flushed each time
+    # the same scan launch alone after a short idle pause (the step loop leaves the GPU power-capped; the kernel is
+    # issue/SFU-bound, so its time follows the SM clock), L2 flushed each time
     iso_ms = None
     try:
+        time.sleep(3.0)
         from dimsum_b200 import selective_scan_cuda
         R_, dt_ = 2 * n, (torch.float32 if args.dtype == "fp32" else torch.bfloat16)
         gi = torch.Generator(device=dev).manual_seed(5)
@@ -373,8 +375,9 @@ def run_b200(args, rank, local_rank, world):
                          "avg_launch_ms": scan_ms, "launches_timed": n_general,
                          "isolated": None if iso_ms is None else
                              {"avg_launch_ms": iso_ms, "frac": by / (iso_ms * 1e-3) / 1e9 / peak,
-                              "note": "identical launch timed alone (general A, L2 flushed): SM clock near max instead of the "
-                                      "power-capped clock it gets between the GEMMs of the step"},
+                              "note": "identical launch (same shapes and strides, general A, L2 flushed) timed alone after a 3 s idle "
+                                      "pause: the gap to avg_launch_ms is the SM clock under sw_power_cap during the step loop, "
+                                      "not interference (tools/layout_probe.py: placement of u/delta/z does not matter)"},
                          "path": "one exp per step (A rows arithmetic, --init-form-fastpath)" if args.init_form_fastpath
                                  else "general A (16 exps per step)",
                          "init_form_A_fastpath": None if fast_ms is None else
