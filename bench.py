@@ -28,10 +28,12 @@ TOTAL_LATENTS = 256
 CFG_SCALE = 4.0
 NUM_GRID = 250
 D_INNER, D_STATE, SEQ = 1024, 16, 256
+RES = 32                         # latent side: 32 (256px, BASELINE configs[2]) or 64 (512px, configs[3]); --px sets RES and SEQ
 CPU_SAMPLE_LATENTS = 8          # bounded CPU sample: batching helps the CPU path (0.18 -> 0.57 latents/s from 1 to 8 on 8 cores)
 
 
-def build_model(device, res=32, seed=0):
+def build_model(device, res=None, seed=0):
+    res = RES if res is None else res
     from dimsum_b200.models_dim import DiM_models
     torch.manual_seed(seed)
     with torch.device(device):
@@ -44,7 +46,8 @@ def build_model(device, res=32, seed=0):
     return model.to(device).eval()    # buffers built from numpy tables are created on the CPU
 
 
-def make_inputs(n_total, res=32, seed=0):
+def make_inputs(n_total, res=None, seed=0):
+    res = RES if res is None else res
     g = torch.Generator().manual_seed(seed)
     z = torch.randn(n_total, 4, res, res, generator=g)
     y = torch.randint(0, 1000, (n_total,), generator=g)
@@ -151,8 +154,8 @@ def run_reference(args, rank):
         "impl": "reference", "metric": "DiMSUM-L/2 fwd latents/s", "value": val, "unit": "latents/s", "n_gpus": args.gpus,
         "steps": len(times), "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "DiMSUM-L/2 256px CFG denoising evaluation (configs[2]), CPU reference path",
-                   "latents_per_step": n, "rows_per_step": 2 * n, "cfg_scale": CFG_SCALE, "tokens": SEQ},
+        "config": {"workload": "DiMSUM-L/2 %dpx CFG denoising evaluation (configs[%d]), CPU reference path" % (8 * RES, 2 if RES == 32 else 3),
+                   "latents_per_step": n, "rows_per_step": 2 * n, "cfg_scale": CFG_SCALE, "tokens": SEQ, "px": 8 * RES},
         "cpu_baseline": {"value": val, "unit": "latents/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": f"{n} latents ({2 * n} CFG rows) x {len(times)} evaluation(s) of the 249-evaluation sampler"},
         "e2e": {"value": val, "unit": "latents/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -347,7 +350,7 @@ def run_b200(args, rank, local_rank, world):
         achieved = by / (scan_ms * 1e-3) / 1e9
         traffic = None
         tr_path = os.path.join(ROOT, "profiles", "scan_fwd_traffic.json")
-        if os.path.exists(tr_path):
+        if os.path.exists(tr_path) and RES == 32 and n == TOTAL_LATENTS:    # the capture was taken at this launch shape
             try:
                 tr = json.load(open(tr_path))
                 traffic = tr.get(args.dtype, {}).get("dram_bytes_per_launch")
@@ -357,13 +360,14 @@ def run_b200(args, rank, local_rank, world):
             "metric": "DiMSUM-L/2 fwd latents/s", "value": n_total / (ms * 1e-3), "unit": "latents/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32" if args.dtype == "fp32" else "bf16", "data": "synthetic",
-            "config": {"workload": "DiMSUM-L/2 256px CFG denoising evaluation (BASELINE configs[2]): 256 latents sharded "
+            "config": {"workload": "DiMSUM-L/2 %dpx CFG denoising evaluation (BASELINE configs[%d]): %d latents sharded "
+                                   % (8 * RES, 2 if RES == 32 else 3, n_total) +
                                    "over the ranks, 2x rows with CFG, one Euler step of the 250-point grid per step",
                        "latents_total": n_total, "rows_per_rank": 2 * n, "tokens": SEQ, "d_inner": D_INNER, "d_state": D_STATE,
                        "cfg_scale": CFG_SCALE, "matmul": "tf32" if args.dtype == "fp32" else "bf16 autocast",
                        "launch": "eager" if graphed is None else "CUDA graph replay (%d launches of this repo's kernels per step)"
                                  % graphed.launches_per_replay,
-                       "l2": "working set per step >> 126 MB L2 (xz alone is %.0f MB per mixer call)" % (2 * n * 2048 * 256 * s / 1e6),
+                       "l2": "working set per step >> 126 MB L2 (xz alone is %.0f MB per mixer call)" % (2 * n * 2 * D_INNER * SEQ * s / 1e6),
                        "params": sum(p.numel() for p in model.parameters())},
             "e2e": {"value": n_total / (ms_e2e * 1e-3), "unit": "latents/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": (x_host.numel() * 4 + y_host.numel() * 8 + t_host.numel() * 4) * world,
@@ -410,12 +414,16 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--latents", type=int, default=TOTAL_LATENTS)
+    ap.add_argument("--px", type=int, default=256, choices=[256, 512], help="image size: 256 (L=256 tokens) or 512 (L=1024, configs[3])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying a CUDA graph")
     ap.add_argument("--init-form-fastpath", action="store_true",
                     help="let the scan use its one-exp-per-step path for arithmetic-progression A.  The random-init benchmark "
                          "model satisfies it (A = -(1..16)), trained checkpoints do not, so the headline runs the GENERAL path")
     args = ap.parse_args()
+    global RES, SEQ
+    RES = args.px // 8
+    SEQ = (RES // 2) ** 2
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

@@ -144,7 +144,9 @@ __global__ void __launch_bounds__(256) conv_fwd_scalar_kernel(const ConvArgs a) 
 constexpr int kBwdThreads = 128;
 constexpr int kBatchPerCta = 8;
 
-template <typename T>
+// kNV = 16-byte vectors per thread on the vector path (2 when the row length allows: halves the halo shuffles and the
+// address arithmetic per element -- the kernel is issue-bound), 0 = scalar path for unaligned / ragged rows
+template <typename T, int kNV, bool kSilu>
 __global__ void __launch_bounds__(kBwdThreads) conv_bwd_kernel(const ConvArgs a) {
     const int d = blockIdx.x;
     const int b0 = blockIdx.y * kBatchPerCta;
@@ -159,79 +161,90 @@ __global__ void __launch_bounds__(kBwdThreads) conv_bwd_kernel(const ConvArgs a)
     const float bias = a.bias != nullptr ? load_w(a.bias, a.w_dtype, d) : 0.f;
     float dw[kMaxW] = {0.f, 0.f, 0.f, 0.f};
     float db = 0.f;
+    // g = dout * act'(pre)
+    auto gate = [&](float gout, float pre) {
+        if (!kSilu) return gout;
+        const float sg = sigmoid_f(pre);
+        return gout * (sg * fmaf(pre, 1.f - sg, 1.f));
+    };
 
     // g[l] = dout[l] * act'(pre[l]);  dx[l] = sum_j w[3-j] g[l+j];  dw[k] += g[l] x[l-3+k]
-    if (a.seqlen % Io<T>::kVec == 0 && a.vec_ok) {
-        // vector path: a thread owns one 16-byte vector; x halo comes from the lane below, g halo from the lane above
-        constexpr int VEC = Io<T>::kVec;
-        const int vpr = L / VEC;
+    if constexpr (kNV > 0) {
+        // vector path: a thread owns kNV consecutive 16-byte vectors; x halo comes from the lane below, g halo from the lane above
+        constexpr int VEC = Io<T>::kVec, E = kNV * VEC;
+        const int ipr = L / E;                                   // items per row
         const int lane = threadIdx.x & 31;
-        const int total = nb * vpr;
+        const int total = nb * ipr;
         for (int base = 0; base < total; base += kBwdThreads) {
             const int idx = base + threadIdx.x;
             const bool act = idx < total;
-            const int bl = act ? idx / vpr : 0, v = act ? idx % vpr : 0;
-            const T *xr = reinterpret_cast<const T *>(a.x) + (b0 + bl) * a.x_bs + d * a.x_ds + v * VEC;
-            const T *gr = reinterpret_cast<const T *>(a.dout) + (b0 + bl) * a.g_bs + d * a.g_ds + v * VEC;
-            float xs[VEC + kMaxW - 1], g[VEC + kMaxW - 1];
+            const int bl = act ? idx / ipr : 0, v = act ? idx % ipr : 0;
+            const int64_t xo = (int64_t)(b0 + bl) * a.x_bs + (int64_t)d * a.x_ds + v * E;
+            const int64_t go = (int64_t)(b0 + bl) * a.g_bs + (int64_t)d * a.g_ds + v * E;
+            const T *xr = reinterpret_cast<const T *>(a.x) + xo;
+            const T *gr = reinterpret_cast<const T *>(a.dout) + go;
+            float xs[E + kMaxW - 1], g[E + kMaxW - 1];
 #pragma unroll
-            for (int i = 0; i < VEC + kMaxW - 1; ++i) { xs[i] = 0.f; g[i] = 0.f; }
+            for (int i = 0; i < E + kMaxW - 1; ++i) { xs[i] = 0.f; g[i] = 0.f; }
             if (act) {
-                Io<T>::ldv(xr, reinterpret_cast<float(&)[VEC]>(xs[kMaxW - 1]));
-                Io<T>::ldv(gr, reinterpret_cast<float(&)[VEC]>(g[0]));
+#pragma unroll
+                for (int j = 0; j < kNV; ++j) {
+                    Io<T>::ldv(xr + j * VEC, reinterpret_cast<float(&)[VEC]>(xs[kMaxW - 1 + j * VEC]));
+                    Io<T>::ldv(gr + j * VEC, reinterpret_cast<float(&)[VEC]>(g[j * VEC]));
+                }
             }
-            const float h0 = __shfl_up_sync(0xffffffffu, xs[VEC + kMaxW - 4], 1);
-            const float h1 = __shfl_up_sync(0xffffffffu, xs[VEC + kMaxW - 3], 1);
-            const float h2 = __shfl_up_sync(0xffffffffu, xs[VEC + kMaxW - 2], 1);
+            const float h0 = __shfl_up_sync(0xffffffffu, xs[E + kMaxW - 4], 1);
+            const float h1 = __shfl_up_sync(0xffffffffu, xs[E + kMaxW - 3], 1);
+            const float h2 = __shfl_up_sync(0xffffffffu, xs[E + kMaxW - 2], 1);
             if (act && v > 0) {
                 if (lane > 0) { xs[0] = h0; xs[1] = h1; xs[2] = h2; }
                 else { xs[0] = Io<T>::ld(xr - 3); xs[1] = Io<T>::ld(xr - 2); xs[2] = Io<T>::ld(xr - 1); }
             }
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) {
-                if (a.silu) {
+            for (int i = 0; i < E; ++i) {
+                if (kSilu) {
                     float pre = bias;
 #pragma unroll
                     for (int k = 0; k < kMaxW; ++k) pre = fmaf(w[k], xs[i + k], pre);
-                    const float sg = sigmoid_f(pre);
-                    g[i] *= sg * fmaf(pre, 1.f - sg, 1.f);
+                    g[i] = gate(g[i], pre);
                 }
                 db += g[i];
 #pragma unroll
                 for (int k = 0; k < kMaxW; ++k) dw[k] = fmaf(g[i], xs[i + k], dw[k]);
             }
-            // first 3 g's of the next vector of the same row
+            // first 3 g's of the next item of the same row
             const float n0 = __shfl_down_sync(0xffffffffu, g[0], 1);
             const float n1 = __shfl_down_sync(0xffffffffu, g[1], 1);
             const float n2 = __shfl_down_sync(0xffffffffu, g[2], 1);
-            if (act && v + 1 < vpr) {
+            if (act && v + 1 < ipr) {
                 if (lane < 31 && idx + 1 < total) {
-                    g[VEC] = n0; g[VEC + 1] = n1; g[VEC + 2] = n2;
+                    g[E] = n0; g[E + 1] = n1; g[E + 2] = n2;
                 } else {   // warp edge: recompute the neighbour's first three g's
 #pragma unroll
                     for (int j = 0; j < kMaxW - 1; ++j) {
-                        float gg = Io<T>::ld(gr + VEC + j);
-                        if (a.silu) {
-                            float pre = bias;
+                        float pre = bias;
+                        if (kSilu) {
 #pragma unroll
-                            for (int k = 0; k < kMaxW; ++k) pre = fmaf(w[k], Io<T>::ld(xr + VEC + j - (kMaxW - 1) + k), pre);
-                            const float sg = sigmoid_f(pre);
-                            gg *= sg * fmaf(pre, 1.f - sg, 1.f);
+                            for (int k = 0; k < kMaxW; ++k) pre = fmaf(w[k], Io<T>::ld(xr + E + j - (kMaxW - 1) + k), pre);
                         }
-                        g[VEC + j] = gg;
+                        g[E + j] = gate(Io<T>::ld(gr + E + j), pre);
                     }
                 }
             }
             if (act) {
-                float dxv[VEC];
+                T *dxr = reinterpret_cast<T *>(a.dx) + (int64_t)(b0 + bl) * a.dx_bs + (int64_t)d * a.dx_ds + v * E;
 #pragma unroll
-                for (int i = 0; i < VEC; ++i) {
-                    float acc = 0.f;
+                for (int j = 0; j < kNV; ++j) {
+                    float dxv[VEC];
 #pragma unroll
-                    for (int j = 0; j < kMaxW; ++j) acc = fmaf(w[kMaxW - 1 - j], g[i + j], acc);
-                    dxv[i] = acc;
+                    for (int i = 0; i < VEC; ++i) {
+                        float acc = 0.f;
+#pragma unroll
+                        for (int k = 0; k < kMaxW; ++k) acc = fmaf(w[kMaxW - 1 - k], g[j * VEC + i + k], acc);
+                        dxv[i] = acc;
+                    }
+                    Io<T>::stv(dxr + j * VEC, dxv);
                 }
-                Io<T>::stv(reinterpret_cast<T *>(a.dx) + (b0 + bl) * a.dx_bs + d * a.dx_ds + v * VEC, dxv);
             }
         }
     } else
@@ -250,14 +263,12 @@ __global__ void __launch_bounds__(kBwdThreads) conv_bwd_kernel(const ConvArgs a)
         for (int j = 0; j < kMaxW; ++j) {   // output position l + j (j = 0 is this thread's own g)
             const int lo = l + j;
             if (lo >= L) break;
-            float g = Io<T>::ld(gr + lo);
-            if (a.silu) {
-                float pre = bias;
+            float pre = bias;
+            if (kSilu) {
 #pragma unroll
                 for (int k = 0; k < kMaxW; ++k) pre = fmaf(w[k], xs[j + k], pre);
-                const float sg = sigmoid_f(pre);
-                g *= sg * fmaf(pre, 1.f - sg, 1.f);
             }
+            const float g = gate(Io<T>::ld(gr + lo), pre);
             dxv = fmaf(w[kMaxW - 1 - j], g, dxv);
             if (j == 0) {
                 db += g;
@@ -313,7 +324,13 @@ int run_fwd(const ConvArgs &a, bool vec_ok, cudaStream_t stream) {
 template <typename T>
 int run_bwd(const ConvArgs &a, cudaStream_t stream) {
     dim3 grid(a.dim, (a.batch + kBatchPerCta - 1) / kBatchPerCta);
-    conv_bwd_kernel<T><<<grid, kBwdThreads, 0, stream>>>(a);
+    auto go = [&](auto kern) { kern<<<grid, kBwdThreads, 0, stream>>>(a); };
+    const int nv = !a.vec_ok ? 0 : (a.seqlen % (2 * Io<T>::kVec) == 0 ? 2 : (a.seqlen % Io<T>::kVec == 0 ? 1 : 0));
+    if (a.silu) {
+        if (nv == 2) go(conv_bwd_kernel<T, 2, true>); else if (nv == 1) go(conv_bwd_kernel<T, 1, true>); else go(conv_bwd_kernel<T, 0, true>);
+    } else {
+        if (nv == 2) go(conv_bwd_kernel<T, 2, false>); else if (nv == 1) go(conv_bwd_kernel<T, 1, false>); else go(conv_bwd_kernel<T, 0, false>);
+    }
     return check_launch("causal_conv1d_bwd");
 }
 

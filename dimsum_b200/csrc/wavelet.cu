@@ -52,7 +52,7 @@ DEV int patch_pixel(int j2, int j1) {
     return row * 4 + col;
 }
 
-constexpr int kWaveThreads = 256;
+constexpr int kWaveThreads = 256;   // upper bound; the launch uses one thread per channel (group of 4), so none idles in the butterfly
 
 // 4 consecutive channels: one 16-byte (fp32) or 8-byte (16-bit) access
 template <typename T> DEV void ld4(const T *p, float (&v)[4]);
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(kWaveThreads) wavelet_kernel(const WaveArgs a)
 
     if (!kInverse) {
         // image tokens -> butterfly -> tile[p1p2][k * Cq + c / 16] -> coefficient tokens at pos[token]
-        for (int c0 = threadIdx.x * CH; c0 < C; c0 += kWaveThreads * CH) {
+        for (int c0 = threadIdx.x * CH; c0 < C; c0 += blockDim.x * CH) {
             float px[16][CH];
 #pragma unroll
             for (int j2 = 0; j2 < 4; ++j2)
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(kWaveThreads) wavelet_kernel(const WaveArgs a)
             }
         }
         __syncthreads();
-        for (int idx = threadIdx.x * CH; idx < 16 * C; idx += kWaveThreads * CH) {
+        for (int idx = threadIdx.x * CH; idx < 16 * C; idx += blockDim.x * CH) {
             const int t16 = idx / C, c = idx % C;
             float v[CH];
             if constexpr (kVec4) {
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(kWaveThreads) wavelet_kernel(const WaveArgs a)
             stc(dst + (int64_t)seq_of(t16) * a.d_ts + c, v);
         }
     } else {
-        for (int idx = threadIdx.x * CH; idx < 16 * C; idx += kWaveThreads * CH) {
+        for (int idx = threadIdx.x * CH; idx < 16 * C; idx += blockDim.x * CH) {
             const int t16 = idx / C, c = idx % C;
             float v[CH];
             ldc(src + (int64_t)seq_of(t16) * a.s_ts + c, v);
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(kWaveThreads) wavelet_kernel(const WaveArgs a)
             }
         }
         __syncthreads();
-        for (int c0 = threadIdx.x * CH; c0 < C; c0 += kWaveThreads * CH) {
+        for (int c0 = threadIdx.x * CH; c0 < C; c0 += blockDim.x * CH) {
             float px[16][CH];
 #pragma unroll
             for (int i = 0; i < CH; ++i) {
@@ -196,7 +196,9 @@ int run_wavelet(const dimsum_wavelet_params *p, bool inverse, cudaStream_t strea
                       a.s_bs % 4 == 0 && a.s_ts % 4 == 0 && a.d_bs % 4 == 0 && a.d_ts % 4 == 0;
     auto go = [&](auto kern) {
         if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        kern<<<grid, kWaveThreads, smem, stream>>>(a);
+        const int per = vec4 ? 4 : 1;
+        const int threads = min(kWaveThreads, max(64, ((a.channels + per - 1) / per + 31) / 32 * 32));
+        kern<<<grid, threads, smem, stream>>>(a);
     };
     if (inverse) {
         if (vec4) go(wavelet_kernel<T, true, true>); else go(wavelet_kernel<T, true, false>);
