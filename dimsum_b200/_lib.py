@@ -113,6 +113,7 @@ WaveletParams = STRUCTS["dimsum_wavelet_params"]
 RowwiseParams = STRUCTS["dimsum_rowwise_params"]
 RmsnormParams = STRUCTS["dimsum_rmsnorm_params"]
 GeluMulParams = STRUCTS["dimsum_gelu_mul_params"]
+NormModulateParams = STRUCTS["dimsum_norm_modulate_params"]
 
 ENTRY_POINTS = {
     "dimsum_selective_scan_fwd": ScanFwdParams,
@@ -126,6 +127,7 @@ ENTRY_POINTS = {
     "dimsum_gate_residual": RowwiseParams,
     "dimsum_add_rmsnorm": RmsnormParams,
     "dimsum_gelu_mul": GeluMulParams,
+    "dimsum_norm_modulate": NormModulateParams,
 }
 
 

@@ -61,11 +61,34 @@ __global__ void __launch_bounds__(256) rowwise_kernel(const dimsum_rowwise_param
     st8(p.dst, (int)p.dst_dtype, b * p.dst_batch_stride + (int64_t)l * p.dst_token_stride + c0, o);
 }
 
-// one warp per row; the row lives in registers between the two passes (channels <= 32 * 16 * VEC per warp loop)
-template <typename T>
-__global__ void __launch_bounds__(256) add_rmsnorm_kernel(const dimsum_rmsnorm_params p) {
+// VEC consecutive channels of a tensor whose dtype is only known at run time (uniform branch)
+template <int VEC>
+DEV void ld_rt(const void *base, int dtype, int64_t idx, float (&v)[VEC]) {
+#pragma unroll
+    for (int i = 0; i < VEC; i += 4) {
+        float (&q)[4] = reinterpret_cast<float(&)[4]>(v[i]);
+        if (dtype == DIMSUM_F32) Io<float>::ld4(reinterpret_cast<const float *>(base) + idx + i, q);
+        else if (dtype == DIMSUM_BF16) Io<__nv_bfloat16>::ld4(reinterpret_cast<const __nv_bfloat16 *>(base) + idx + i, q);
+        else Io<__half>::ld4(reinterpret_cast<const __half *>(base) + idx + i, q);
+    }
+}
+template <int VEC>
+DEV void st_rt(void *base, int dtype, int64_t idx, const float (&v)[VEC]) {
+#pragma unroll
+    for (int i = 0; i < VEC; i += 4) {
+        const float (&q)[4] = reinterpret_cast<const float(&)[4]>(v[i]);
+        if (dtype == DIMSUM_F32) Io<float>::st4(reinterpret_cast<float *>(base) + idx + i, q);
+        else if (dtype == DIMSUM_BF16) Io<__nv_bfloat16>::st4(reinterpret_cast<__nv_bfloat16 *>(base) + idx + i, q);
+        else Io<__half>::st4(reinterpret_cast<__half *>(base) + idx + i, q);
+    }
+}
+
+// residual add + RMSNorm / LayerNorm (+ adaLN modulate): one warp per row, the row lives in registers between the
+// passes (channels <= 32 lanes * 8 * VEC: 1024 fp32, 2048 16-bit)
+template <typename T, bool kLayerNorm>
+__global__ void __launch_bounds__(256) norm_kernel(const dimsum_norm_modulate_params p) {
     constexpr int VEC = Io<T>::kVec;
-    constexpr int kMaxIter = 8;                       // up to 32 lanes * 8 * VEC channels (1024 fp32, 2048 16-bit)
+    constexpr int kMaxIter = 8;
     const int warp = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
     if (warp >= p.rows) return;
@@ -74,7 +97,7 @@ __global__ void __launch_bounds__(256) add_rmsnorm_kernel(const dimsum_rmsnorm_p
     const float *res = p.residual != nullptr ? reinterpret_cast<const float *>(p.residual) + (int64_t)warp * p.channels : nullptr;
     float *res_out = p.res_out != nullptr ? reinterpret_cast<float *>(p.res_out) + (int64_t)warp * p.channels : nullptr;
     float vals[kMaxIter][VEC];
-    float ss = 0.f;
+    float ss = 0.f, sum = 0.f;
 #pragma unroll
     for (int it = 0; it < kMaxIter; ++it) {
         const int v = lane + it * 32;
@@ -94,24 +117,80 @@ __global__ void __launch_bounds__(256) add_rmsnorm_kernel(const dimsum_rmsnorm_p
                         make_float4(vals[it][i], vals[it][i + 1], vals[it][i + 2], vals[it][i + 3]);
             }
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) ss = fmaf(vals[it][i], vals[it][i], ss);
+            for (int i = 0; i < VEC; ++i) {
+                if (kLayerNorm) sum += vals[it][i];
+                else ss = fmaf(vals[it][i], vals[it][i], ss);
+            }
+        }
+    }
+    float mean = 0.f;
+    if (kLayerNorm) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        mean = sum / (float)p.channels;
+#pragma unroll
+        for (int it = 0; it < kMaxIter; ++it) {
+            if (lane + it * 32 < nvec) {
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) { vals[it][i] -= mean; ss = fmaf(vals[it][i], vals[it][i], ss); }
+            }
         }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
     const float rstd = rsqrtf(ss / (float)p.channels + p.eps);
     const float *w = reinterpret_cast<const float *>(p.weight);
-    T *y = reinterpret_cast<T *>(p.y) + (int64_t)warp * p.y_row_stride;
+    const int64_t mrow = (warp / p.rows_per_batch) * p.vec_row_stride;
+    const int64_t yrow = (int64_t)warp * p.y_row_stride;
 #pragma unroll
     for (int it = 0; it < kMaxIter; ++it) {
         const int v = lane + it * 32;
         if (v < nvec) {
             float o[VEC];
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) o[i] = vals[it][i] * rstd * w[v * VEC + i];
-            Io<T>::stv(y + v * VEC, o);
+            for (int i = 0; i < VEC; ++i) o[i] = vals[it][i] * rstd;
+            if (!kLayerNorm) {
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) o[i] *= w[v * VEC + i];
+            }
+            if (p.scale != nullptr) {
+                float sh[VEC], sc[VEC];
+                ld_rt<VEC>(p.shift, (int)p.aux_dtype, mrow + v * VEC, sh);
+                ld_rt<VEC>(p.scale, (int)p.aux_dtype, mrow + v * VEC, sc);
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) o[i] = fmaf(o[i], 1.f + sc[i], sh[i]);
+            }
+            st_rt<VEC>(p.y, (int)p.y_dtype, yrow + v * VEC, o);
         }
     }
+}
+
+int run_norm(const dimsum_norm_modulate_params *p, cudaStream_t stream, const char *who) {
+    DIMSUM_REQUIRE(p != nullptr && p->x && p->y, DIMSUM_ERR_INVALID, "%s: null pointer", who);
+    DIMSUM_REQUIRE(p->rows >= 0 && p->channels > 0, DIMSUM_ERR_INVALID, "%s: bad sizes", who);
+    DIMSUM_REQUIRE(p->x_dtype >= 0 && p->x_dtype <= 2 && p->y_dtype >= 0 && p->y_dtype <= 2, DIMSUM_ERR_INVALID, "%s: unknown dtype", who);
+    DIMSUM_REQUIRE(p->norm_kind == 0 || p->norm_kind == 1, DIMSUM_ERR_INVALID, "%s: unknown norm_kind", who);
+    DIMSUM_REQUIRE(p->norm_kind == 1 || p->weight != nullptr, DIMSUM_ERR_INVALID, "%s: RMSNorm needs a weight", who);
+    DIMSUM_REQUIRE((p->shift == nullptr) == (p->scale == nullptr), DIMSUM_ERR_INVALID, "%s: shift and scale go together", who);
+    DIMSUM_REQUIRE(p->scale == nullptr || (p->rows_per_batch > 0 && p->aux_dtype >= 0 && p->aux_dtype <= 2), DIMSUM_ERR_INVALID,
+                   "%s: modulate needs rows_per_batch and aux_dtype", who);
+    const int vec = p->x_dtype == DIMSUM_F32 ? 4 : 8;
+    DIMSUM_REQUIRE(p->channels % vec == 0 && p->channels <= 32 * 8 * vec, DIMSUM_ERR_UNSUPPORTED,
+                   "%s: channels=%lld must be a multiple of %d and at most %d", who, (long long)p->channels, vec, 32 * 8 * vec);
+    DIMSUM_REQUIRE(aligned16(p->x) && aligned16(p->y) && p->x_row_stride % vec == 0 && p->y_row_stride % 4 == 0 &&
+                       (p->residual == nullptr || aligned16(p->residual)) && (p->res_out == nullptr || aligned16(p->res_out)) &&
+                       (p->scale == nullptr || (aligned16(p->shift) && aligned16(p->scale) && p->vec_row_stride % 4 == 0)),
+                   DIMSUM_ERR_UNSUPPORTED, "%s: rows must be 16-byte aligned", who);
+    if (p->rows == 0) return DIMSUM_OK;
+    const unsigned blocks = (unsigned)((p->rows * 32 + 255) / 256);
+#define NK(T)                                                                  \
+    if (p->norm_kind == 1) norm_kernel<T, true><<<blocks, 256, 0, stream>>>(*p); \
+    else norm_kernel<T, false><<<blocks, 256, 0, stream>>>(*p);
+    if (p->x_dtype == DIMSUM_F32) { NK(float) }
+    else if (p->x_dtype == DIMSUM_BF16) { NK(__nv_bfloat16) }
+    else { NK(__half) }
+#undef NK
+    return check_launch(who);
 }
 
 // tanh-approximated GELU with an accurate tanh: tanh(y) = 1 - 2 / (exp(2y) + 1)
@@ -176,22 +255,24 @@ extern "C" int dimsum_gate_residual(const dimsum_rowwise_params *p, void *stream
 
 extern "C" int dimsum_add_rmsnorm(const dimsum_rmsnorm_params *p, void *stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-    if (p != nullptr && p->rows == 0) return DIMSUM_OK;
-    DIMSUM_REQUIRE(p != nullptr && p->x && p->weight && p->y, DIMSUM_ERR_INVALID, "add_rmsnorm: null pointer");
-    DIMSUM_REQUIRE(p->rows >= 0 && p->channels > 0, DIMSUM_ERR_INVALID, "add_rmsnorm: bad sizes");
-    DIMSUM_REQUIRE(p->dtype >= 0 && p->dtype <= 2, DIMSUM_ERR_INVALID, "add_rmsnorm: unknown dtype");
-    const int vec = p->dtype == DIMSUM_F32 ? 4 : 8;
-    DIMSUM_REQUIRE(p->channels % vec == 0 && p->channels <= 32 * 8 * vec, DIMSUM_ERR_UNSUPPORTED,
-                   "add_rmsnorm: channels %lld not supported (multiple of %d, at most %d)", (long long)p->channels, vec, 32 * 8 * vec);
-    DIMSUM_REQUIRE(aligned16(p->x) && aligned16(p->y) && p->x_row_stride % vec == 0 && p->y_row_stride % vec == 0 &&
-                       (p->residual == nullptr || aligned16(p->residual)) && (p->res_out == nullptr || aligned16(p->res_out)),
-                   DIMSUM_ERR_UNSUPPORTED, "add_rmsnorm: rows must be 16-byte aligned");
+    DIMSUM_REQUIRE(p != nullptr, DIMSUM_ERR_INVALID, "add_rmsnorm: null params");
     if (p->rows == 0) return DIMSUM_OK;
-    const unsigned blocks = (unsigned)((p->rows * 32 + 255) / 256);
-    if (p->dtype == DIMSUM_F32) add_rmsnorm_kernel<float><<<blocks, 256, 0, stream>>>(*p);
-    else if (p->dtype == DIMSUM_BF16) add_rmsnorm_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(*p);
-    else add_rmsnorm_kernel<__half><<<blocks, 256, 0, stream>>>(*p);
-    return check_launch("add_rmsnorm");
+    dimsum_norm_modulate_params q{};
+    q.rows = p->rows; q.channels = p->channels; q.rows_per_batch = 1;
+    q.x_dtype = p->dtype; q.y_dtype = p->dtype; q.aux_dtype = DIMSUM_F32; q.norm_kind = 0;
+    q.x_row_stride = p->x_row_stride; q.y_row_stride = p->y_row_stride; q.vec_row_stride = 0;
+    q.x = p->x; q.residual = p->residual; q.weight = p->weight; q.shift = nullptr; q.scale = nullptr;
+    q.y = p->y; q.res_out = p->res_out; q.eps = p->eps;
+    DIMSUM_REQUIRE(p->dtype >= 0 && p->dtype <= 2, DIMSUM_ERR_INVALID, "add_rmsnorm: bad arguments");
+    const int vec = p->dtype == DIMSUM_F32 ? 4 : 8;
+    DIMSUM_REQUIRE(p->y_row_stride % vec == 0, DIMSUM_ERR_UNSUPPORTED, "add_rmsnorm: rows must be 16-byte aligned");
+    return run_norm(&q, stream, "add_rmsnorm");
+}
+
+extern "C" int dimsum_norm_modulate(const dimsum_norm_modulate_params *p, void *stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (p != nullptr && p->rows == 0) return DIMSUM_OK;
+    return run_norm(p, stream, "norm_modulate");
 }
 
 extern "C" int dimsum_gelu_mul(const dimsum_gelu_mul_params *p, void *stream_) {

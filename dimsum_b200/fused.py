@@ -94,6 +94,42 @@ def add_rmsnorm(x, residual, weight, eps, want_residual=True):
     return y.view(shape), (res_out.view(shape) if res_out is not None else None)
 
 
+def norm_modulate(x, residual, weight, eps, shift, scale, layer_norm=False, out_dtype=None, want_residual=False):
+    """-> (y, res_out).  h = x + residual (fp32); n = RMSNorm(h) * weight, or LayerNorm(h) without affine when
+    `layer_norm`; y = n * (1 + scale[b]) + shift[b] in `out_dtype` (default x.dtype); res_out = h (fp32) on request.
+    One pass for `hidden = hidden + x; modulate(norm_2(hidden), shift, scale)` (models_dim.py:1509-1512) and for
+    `modulate(LayerNorm(x), shift, scale)` of the shared DiT block / final layer (models_dim.py:1079-1098)."""
+    B, L, C = x.shape
+    x2 = x.reshape(-1, C)
+    if x2.stride(1) != 1:
+        x2 = x2.contiguous()
+    if residual is not None:
+        if residual.dtype != torch.float32 or residual.shape != x.shape:
+            raise RuntimeError("norm_modulate: residual must be fp32 with the shape of x")
+        residual = residual.contiguous()
+    if shift.shape != (B, C) or scale.shape != (B, C) or shift.dtype != scale.dtype:
+        raise RuntimeError("norm_modulate: shift / scale must be (batch, channels) of one dtype")
+    if shift.stride(1) != 1 or scale.stride(1) != 1 or shift.stride(0) != scale.stride(0):
+        shift, scale = shift.contiguous(), scale.contiguous()
+    out_dtype = out_dtype or x.dtype
+    y = torch.empty((B * L, C), device=x.device, dtype=out_dtype)
+    res_out = torch.empty((B * L, C), device=x.device, dtype=torch.float32) if want_residual else None
+    w = None if layer_norm else weight.float().contiguous()
+    with torch.cuda.device(x.device):
+        p = _lib.NormModulateParams()
+        p.rows, p.channels, p.rows_per_batch = B * L, C, L
+        p.x_dtype, p.aux_dtype, p.y_dtype, p.norm_kind = _DT[x.dtype], _DT[shift.dtype], _DT[out_dtype], int(layer_norm)
+        p.x_row_stride, p.y_row_stride, p.vec_row_stride = x2.stride(0), y.stride(0), shift.stride(0)
+        p.x, p.y = x2.data_ptr(), y.data_ptr()
+        p.weight = w.data_ptr() if w is not None else None
+        p.shift, p.scale = shift.data_ptr(), scale.data_ptr()
+        p.residual = residual.data_ptr() if residual is not None else None
+        p.res_out = res_out.data_ptr() if res_out is not None else None
+        p.eps = eps
+        _lib.call("dimsum_norm_modulate", p, torch.cuda.current_stream(x.device).cuda_stream)
+    return y.view(B, L, C), (res_out.view(B, L, C) if res_out is not None else None)
+
+
 def gelu_mul(x12):
     """GatedMLP activation: gelu_tanh(x12[..., :H]) * x12[..., H:] in one pass (dimsum/mlp.py:65-70)."""
     shape = x12.shape

@@ -47,6 +47,20 @@ def _mod(x, shift, scale, idx=None):
     return modulate(x, shift, scale)
 
 
+def _norm_mod(norm, x, shift, scale, residual=None):
+    """modulate(norm(x + residual), shift, scale) -> (modulated, x + residual); one kernel when nothing is recorded."""
+    is_rms = isinstance(norm, RMSNorm)
+    if (_fused_ok(x) and x.dim() == 3 and x.dtype in (torch.float32, torch.bfloat16, torch.float16)
+            and (residual is None or residual.dtype == torch.float32)
+            and (is_rms or (isinstance(norm, nn.LayerNorm) and norm.weight is None and norm.bias is None))):
+        out_dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else None
+        y, h = fused.norm_modulate(x, residual, norm.weight if is_rms else None, norm.eps, shift, scale,
+                                   layer_norm=not is_rms, out_dtype=out_dtype, want_residual=residual is not None)
+        return y, (h if residual is not None else x)
+    h = x if residual is None else x + residual
+    return _mod(norm(h), shift, scale), h
+
+
 def _gated(x, gate, m, idx=None, feeds_gemm=False):
     if _fused_ok(x):
         if m.dtype != gate.dtype:
@@ -247,9 +261,9 @@ class DiMBlockCombined(nn.Module):
         hidden_states, residual = self.norm(hidden_states, residual=residual, prenorm=True, residual_in_fp32=True)
         x1, x2 = hidden_states.chunk(2, dim=2)
         x = self.proj(self.spatial_mamba(x1, c), self.freq_mamba(x2, c))
-        hidden_states = hidden_states + x
         shift, scale, gate = self.adaLN_modulation(c).chunk(3, dim=1)
-        hidden_states = _gated(hidden_states, gate, self.mlp(_mod(self.norm_2(hidden_states), shift, scale)))
+        m, hidden_states = _norm_mod(self.norm_2, x, shift, scale, residual=hidden_states)      # hidden + x, norm_2, modulate
+        hidden_states = _gated(hidden_states, gate, self.mlp(m))
         return hidden_states, residual
 
 
@@ -264,8 +278,8 @@ class DiTBlock(nn.Module):
 
     def forward(self, x, c):
         s1, sc1, g1, s2, sc2, g2 = self.adaLN_modulation(c).chunk(6, dim=1)
-        x = _gated(x, g1, self.attn(_mod(self.norm1(x), s1, sc1)))
-        return _gated(x, g2, self.mlp(_mod(self.norm2(x), s2, sc2)))
+        x = _gated(x, g1, self.attn(_norm_mod(self.norm1, x, s1, sc1)[0]))
+        return _gated(x, g2, self.mlp(_norm_mod(self.norm2, x, s2, sc2)[0]))
 
 
 class FinalLayer(nn.Module):
@@ -277,7 +291,7 @@ class FinalLayer(nn.Module):
 
     def forward(self, x, c):
         shift, scale = self.adaLN_modulation(c).chunk(2, dim=1)
-        return self.linear(_mod(self.norm_final(x), shift, scale))
+        return self.linear(_norm_mod(self.norm_final, x, shift, scale)[0])
 
 
 def get_2d_sincos_pos_embed(embed_dim, grid_size):

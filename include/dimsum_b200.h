@@ -220,6 +220,26 @@ typedef struct {
 
 int dimsum_add_rmsnorm(const dimsum_rmsnorm_params *p, void *stream);
 
+/* residual-add + norm + adaLN modulate in one pass, for the two places a DiMSUM block runs them back to back
+ * (dimsum/models_dim.py:1509-1512: `hidden = hidden + x; mlp(modulate(norm_2(hidden), shift, scale))`, and
+ * :1079-1098 / :1532-1554: `modulate(LayerNorm(x), shift, scale)` of the shared DiT block and the final layer):
+ *     h = x + residual (fp32; residual may be NULL)        res_out = h (fp32, may be NULL)
+ *     n = h * rsqrt(mean(h^2) + eps) * weight              (norm_kind 0, RMSNorm, maths of rms_norm_ref layernorm.py:32-47)
+ *     n = (h - mean(h)) * rsqrt(var(h) + eps)              (norm_kind 1, LayerNorm without affine, biased variance)
+ *     y = n * (1 + scale[row / rows_per_batch]) + shift[row / rows_per_batch]      (shift = scale = NULL: y = n)
+ * x (rows, channels) x_dtype; shift / scale (batch, channels) aux_dtype with row stride vec_row_stride; y y_dtype.
+ */
+typedef struct {
+    int64_t rows, channels, rows_per_batch;
+    int64_t x_dtype, aux_dtype, y_dtype, norm_kind;
+    int64_t x_row_stride, y_row_stride, vec_row_stride;
+    const void *x, *residual, *weight, *shift, *scale;
+    void *y, *res_out;
+    float eps;
+} dimsum_norm_modulate_params;
+
+int dimsum_norm_modulate(const dimsum_norm_modulate_params *p, void *stream);
+
 /* GatedMLP inner activation (dimsum/mlp.py:65-70): y[r, :] = gelu_tanh(x[r, :H]) * x[r, H:2H]; x (rows, 2H), y (rows, H). */
 typedef struct {
     int64_t rows, hidden, dtype;

@@ -62,3 +62,48 @@ def test_gelu_mul(dtype):
     a, b = x.float().chunk(2, dim=-1)
     want = torch.nn.functional.gelu(a, approximate="tanh") * b
     assert rel_err(fused.gelu_mul(x), want) <= (2e-6 if dtype == torch.float32 else 1e-2)
+
+
+@pytest.mark.parametrize("layer_norm", [False, True])
+@pytest.mark.parametrize("x_dtype,aux_dtype,out_dtype", [(torch.float32, torch.float32, None),
+                                                         (torch.bfloat16, torch.bfloat16, torch.bfloat16),
+                                                         (torch.float32, torch.bfloat16, torch.bfloat16)])
+def test_norm_modulate(layer_norm, x_dtype, aux_dtype, out_dtype):
+    """hidden + x -> RMSNorm / LayerNorm -> adaLN modulate in one pass vs the three reference steps
+    (models_dim.py:1509-1512, :1079-1098), including the mixed precisions autocast produces."""
+    import torch.nn.functional as F
+    from dimsum_b200 import fused
+    from oracle import ref_ops
+    g = torch.Generator().manual_seed(3)
+    B, L, C = 3, 37, 1024
+    x = torch.randn(B, L, C, generator=g).to(x_dtype)
+    res = torch.randn(B, L, C, generator=g)
+    w = 1 + 0.1 * torch.randn(C, generator=g)
+    ada = (0.5 * torch.randn(B, 2 * C, generator=g)).to(aux_dtype)
+    shift, scale = ada.chunk(2, dim=1)                                         # row-strided views, as in the model
+    for residual in (res, None):
+        h = x.float() + (residual if residual is not None else 0)
+        n = F.layer_norm(h, (C,), eps=1e-6) if layer_norm else ref_ops.rms_norm_oracle(h, w, eps=1e-6)
+        want = n * (1 + scale.float().unsqueeze(1)) + shift.float().unsqueeze(1)
+        y, r = fused.norm_modulate(x.cuda(), residual.cuda() if residual is not None else None, None if layer_norm else w.cuda(),
+                                   1e-6, shift.cuda(), scale.cuda(), layer_norm=layer_norm, out_dtype=out_dtype,
+                                   want_residual=residual is not None)
+        assert y.dtype == (out_dtype or x_dtype)
+        assert rel_err(y, want) <= (3e-6 if y.dtype == torch.float32 else 1e-2)
+        if residual is not None:
+            assert r.dtype == torch.float32 and rel_err(r, h) <= 1e-6
+        else:
+            assert r is None
+
+
+def test_norm_modulate_rejects_bad_arguments():
+    from dimsum_b200 import fused
+    x = torch.randn(2, 8, 64, device="cuda")
+    sh = torch.randn(2, 64, device="cuda")
+    with pytest.raises(RuntimeError):
+        fused.norm_modulate(x, x.half(), torch.ones(64, device="cuda"), 1e-5, sh, sh)          # residual must be fp32
+    with pytest.raises(RuntimeError):
+        fused.norm_modulate(x, None, torch.ones(64, device="cuda"), 1e-5, sh[:1], sh[:1])      # one shift row per batch row
+    with pytest.raises(NotImplementedError):
+        big = torch.randn(1, 2, 4096, device="cuda")
+        fused.norm_modulate(big, None, torch.ones(4096, device="cuda"), 1e-5, big[:, 0], big[:, 0])   # > 1024 fp32 channels
