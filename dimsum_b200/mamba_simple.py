@@ -101,6 +101,8 @@ class Mamba(nn.Module):
         the host once per parameter version (one sync), then cached; DIMSUM_SCAN_ARITH=0 disables the shortcut."""
         if os.environ.get("DIMSUM_SCAN_ARITH", "1") == "0":
             return False
+        if torch.is_grad_enabled() and self.A_log.requires_grad:
+            return False      # training: A changes every optimizer step, the check would cost one host sync per mixer per step
         key = (self.A_log._version, A.device)
         if key != self._arith_key:
             self._arith_flag = selective_scan_cuda.rows_are_arithmetic(A)

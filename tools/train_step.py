@@ -36,6 +36,7 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--model", default="DiM-L/2")
     ap.add_argument("--depth", type=int, default=None, help="override depth (smoke runs)")
+    ap.add_argument("--profile", default=None, help="write a torch.profiler kernel table of one extra step to this file")
     args = ap.parse_args()
     rank, local, world = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("LOCAL_RANK", 0), ("WORLD_SIZE", 1)))
     dev = torch.device("cuda", local)
@@ -86,6 +87,13 @@ def main():
     ms = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if args.profile and rank == 0:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            step()
+            torch.cuda.synchronize()
+        with open(args.profile, "w") as f:
+            f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=90))
     if rank == 0:
         print(json.dumps({"metric": "DiMSUM-L/2 train latents/s", "value": args.batch * world / (ms.item() * 1e-3),
                           "ms_per_step": ms.item(), "n_gpus": world, "per_gpu_batch": args.batch, "dtype": args.dtype,
