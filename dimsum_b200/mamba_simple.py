@@ -91,8 +91,9 @@ class Mamba(nn.Module):
             order = table
         if order is not None and torch.is_grad_enabled():
             # training through an explicit order: gather token rows (coalesced), run the plain composite, gather back
-            from .scanning_orders import permute_tokens, reverse_permut_np
-            inv = torch.from_numpy(reverse_permut_np(order.cpu().numpy())).to(device=order.device, dtype=torch.int32)
+            from .scanning_orders import permute_tokens
+            inv = torch.empty_like(order)                       # inverse permutation on the device: no host round trip
+            inv[order.long()] = torch.arange(order.numel(), device=order.device, dtype=order.dtype)
             return permute_tokens(self._mix(permute_tokens(hidden_states.contiguous(), order, inv), None), inv, order)
         return self._mix(hidden_states, order)
 

@@ -36,6 +36,9 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--model", default="DiM-L/2")
     ap.add_argument("--depth", type=int, default=None, help="override depth (smoke runs)")
+    ap.add_argument("--graph", action="store_true",
+                    help="capture forward + backward + clip + AdamW of one step in a CUDA graph and replay it (single GPU): the "
+                         "step is ~3000 launches for 86 ms of device work, so eager execution is host-bound")
     ap.add_argument("--profile", default=None, help="write a torch.profiler kernel table of one extra step to this file")
     args = ap.parse_args()
     rank, local, world = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("LOCAL_RANK", 0), ("WORLD_SIZE", 1)))
@@ -55,15 +58,19 @@ def main():
                 p.normal_(0, 0.02)
     model = model.to(dev).train()
     ddp = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local]) if world > 1 else model
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0)
+    use_graph = args.graph and world == 1
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0, capturable=use_graph)
     g = torch.Generator(device=dev).manual_seed(rank)
     amp = torch.autocast("cuda", dtype=torch.bfloat16, enabled=args.dtype == "bf16")
 
-    def step():
+    def draw():
         x1 = torch.randn(args.batch, 4, 32, 32, generator=g, device=dev)
         y = torch.randint(0, 1000, (args.batch,), generator=g, device=dev)
         t = torch.rand(args.batch, generator=g, device=dev)
-        xt, ut = gvp_plan(t, torch.randn(x1.shape, generator=g, device=dev), x1)
+        return x1, torch.randn(x1.shape, generator=g, device=dev), y, t
+
+    def train_on(x1, x0, y, t):
+        xt, ut = gvp_plan(t, x0, x1)
         with amp:
             out = ddp(xt, t, y)
         loss = (out.float() - ut).square().mean()
@@ -72,6 +79,28 @@ def main():
         torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
         opt.step()
         return loss
+
+    if use_graph:
+        static = [b.clone() for b in draw()]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                       # warm-up on a side stream, as graph capture requires
+            for _ in range(3):
+                train_on(*static)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        opt.zero_grad(set_to_none=True)
+        with torch.cuda.graph(graph):
+            static_loss = train_on(*static)
+
+        def step():
+            for dst, src in zip(static, draw()):
+                dst.copy_(src)
+            graph.replay()
+            return static_loss
+    else:
+        def step():
+            return train_on(*draw())
 
     for _ in range(args.warmup):
         step()
@@ -97,6 +126,7 @@ def main():
     if rank == 0:
         print(json.dumps({"metric": "DiMSUM-L/2 train latents/s", "value": args.batch * world / (ms.item() * 1e-3),
                           "ms_per_step": ms.item(), "n_gpus": world, "per_gpu_batch": args.batch, "dtype": args.dtype,
+                          "launch": "CUDA graph replay" if use_graph else "eager",
                           "loss": float(loss), "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30,
                           "missing_grads": [n for n, p in model.named_parameters() if p.grad is None and "cond_proj" not in n]}))
     if world > 1:
