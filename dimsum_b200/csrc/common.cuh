@@ -68,35 +68,6 @@ DEV float rcp_mufu(float x) {
     return y;
 }
 
-// 2^x for x <= 0 on the FMA/ALU pipes (relieves the 16-lane/clk/SM MUFU unit).
-// Cody-Waite split with the 1.5*2^23 magic constant, degree-DEG polynomial with p(0) == 1 exactly
-// so that long-memory decays (x -> 0) do not drift, exponent re-inserted by integer add.
-template <int DEG>
-DEV float2 ex2_poly2(float2 x) {
-    const float kMagic = 12582912.0f;
-    x.x = fmaxf(x.x, -125.0f);
-    x.y = fmaxf(x.y, -125.0f);
-    float2 t = add2(x, splat2(kMagic));
-    float2 f = add2(x, add2(splat2(kMagic), make_float2(-t.x, -t.y)));   // x - round(x), in [-0.5, 0.5]
-    float2 q;
-    if (DEG == 5) {
-        // constrained minimax fit of (2^f-1)/f on [-0.5,0.5]: max rel err of 2^f 1.9e-7 in fp32 Horner
-        q = splat2(1.3264726986e-3f);
-        q = fma2(q, f, splat2(9.6715127576e-3f));
-        q = fma2(q, f, splat2(5.5507337438e-2f));
-        q = fma2(q, f, splat2(2.4022242083e-1f));
-        q = fma2(q, f, splat2(6.9314697760e-1f));
-    } else {  // DEG == 3 (16-bit outputs): max rel err 1.0e-4
-        q = splat2(5.5008930160e-2f);
-        q = fma2(q, f, splat2(2.4221096370e-1f));
-        q = fma2(q, f, splat2(6.9328292723e-1f));
-    }
-    float2 p = fma2(q, f, splat2(1.0f));
-    p.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23));
-    p.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23));
-    return p;
-}
-
 // softplus(x) = max(x,0) + log1p(exp(-|x|)),  log1p(w) = 2 atanh(w/(2+w)), w in (0,1].
 // Agrees with the reference's `x <= 20 ? log1pf(expf(x)) : x` (selective_scan_fwd_kernel.cuh:153-156)
 // to ~1e-7 relative over the whole range (for x > 20 the log term is below half an ulp of x).
