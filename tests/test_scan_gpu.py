@@ -108,6 +108,38 @@ def test_full_size_properties_config2():
     assert torch.equal(y4, y1[5:9])
 
 
+def test_backward_full_size_properties_config2():
+    """B=256, D=2048, L=256, N=16 fp32: the backward is linear in dout, independent across batch rows, and its du matches
+    a central finite difference of the forward along a random direction (size-independent checks of the full grid)."""
+    from dimsum_b200 import selective_scan_cuda
+    R, D, L, N = 256, 2048, 256, 16
+    g = torch.Generator(device="cuda").manual_seed(1)
+    u = torch.randn(R, D, L, generator=g, device="cuda")
+    delta = 0.5 * torch.rand(R, D, L, generator=g, device="cuda")
+    z = torch.randn(R, D, L, generator=g, device="cuda")
+    A = -0.5 * torch.rand(D, N, generator=g, device="cuda") - 0.05
+    Bm, Cm = torch.randn(R, 1, N, L, generator=g, device="cuda"), torch.randn(R, 1, N, L, generator=g, device="cuda")
+    Dv, bias = torch.randn(D, generator=g, device="cuda"), torch.rand(D, generator=g, device="cuda") - 1.0
+    out, x, out_z = selective_scan_cuda.fwd(u, delta, A, Bm, Cm, Dv, z, bias, True)
+    g1, g2 = torch.randn(R, D, L, generator=g, device="cuda"), torch.randn(R, D, L, generator=g, device="cuda")
+    bwd = lambda go, sl=slice(None): selective_scan_cuda.bwd(u[sl], delta[sl], A, Bm[sl], Cm[sl], Dv, z[sl], bias, go, x[sl],
+                                                            out[sl], None, True, False)
+    r1, r2, r12 = bwd(g1), bwd(g2), bwd(g1 + g2)
+    for name, a, b_, c in zip(("du", "ddelta", "dA", "dB", "dC", "dD", "ddelta_bias", "dz"), r1, r2, r12):
+        assert rel_err(c, a + b_) <= 2e-5, name
+    part = bwd(g1[7:11].contiguous(), slice(7, 11))
+    assert rel_err(part[0], r1[0][7:11]) <= 1e-6 and rel_err(part[7], r1[7][7:11]) <= 1e-6      # du, dz of a batch slice
+    assert rel_err(part[3], r1[3][7:11]) <= 1e-5                                                # dB (atomics: order varies)
+    # <du, v> against (f(u + eps v) - f(u - eps v)) / (2 eps) . g1 in fp64 accumulation
+    v = torch.randn(R, D, L, generator=g, device="cuda")
+    eps = 1e-2
+    fp = selective_scan_cuda.fwd(u + eps * v, delta, A, Bm, Cm, Dv, z, bias, True, need_out=False, need_x=False)[2]
+    fm = selective_scan_cuda.fwd(u - eps * v, delta, A, Bm, Cm, Dv, z, bias, True, need_out=False, need_x=False)[2]
+    fd = ((fp.double() - fm.double()) * g1.double()).sum() / (2 * eps)       # the scan is linear in u: exact up to rounding
+    an = (r1[0].double() * v.double()).sum()
+    assert abs(fd - an) <= 1e-4 * abs(an), (float(fd), float(an))
+
+
 def test_reference_error_behaviour():
     from dimsum_b200 import selective_scan_fn
     u = torch.randn(1, 4, 16, device="cuda")
