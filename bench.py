@@ -121,6 +121,11 @@ def scan_bytes(rows, s):
     return s * (4 * rows * D_INNER * SEQ + 2 * rows * D_STATE * SEQ) + 4 * (D_INNER * D_STATE + 2 * D_INNER)
 
 
+def workload_name(n_total):
+    return ("DiMSUM-L/2 %dpx CFG denoising evaluation (BASELINE configs[%d]): %d latents sharded over the ranks, 2x rows with "
+            "CFG, one Euler step of the 250-point grid per step" % (8 * RES, 2 if RES == 32 else 3, n_total))
+
+
 def cpu_reference_step(sd, n_latents, seed=0):
     """One CFG denoising evaluation of the oracle port on the host cores; returns seconds."""
     from oracle import ref_model
@@ -154,7 +159,7 @@ def run_reference(args, rank):
         "impl": "reference", "metric": "DiMSUM-L/2 fwd latents/s", "value": val, "unit": "latents/s", "n_gpus": args.gpus,
         "steps": len(times), "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "DiMSUM-L/2 %dpx CFG denoising evaluation (configs[%d]), CPU reference path" % (8 * RES, 2 if RES == 32 else 3),
+        "config": {"workload": workload_name(args.latents), "impl": "reference CPU path (oracle port), bounded sample per step",
                    "latents_per_step": n, "rows_per_step": 2 * n, "cfg_scale": CFG_SCALE, "tokens": SEQ, "px": 8 * RES},
         "cpu_baseline": {"value": val, "unit": "latents/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": f"{n} latents ({2 * n} CFG rows) x {len(times)} evaluation(s) of the 249-evaluation sampler"},
@@ -360,9 +365,7 @@ def run_b200(args, rank, local_rank, world):
             "metric": "DiMSUM-L/2 fwd latents/s", "value": n_total / (ms * 1e-3), "unit": "latents/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32" if args.dtype == "fp32" else "bf16", "data": "synthetic",
-            "config": {"workload": "DiMSUM-L/2 %dpx CFG denoising evaluation (BASELINE configs[%d]): %d latents sharded "
-                                   % (8 * RES, 2 if RES == 32 else 3, n_total) +
-                                   "over the ranks, 2x rows with CFG, one Euler step of the 250-point grid per step",
+            "config": {"workload": workload_name(n_total),
                        "latents_total": n_total, "rows_per_rank": 2 * n, "tokens": SEQ, "d_inner": D_INNER, "d_state": D_STATE,
                        "cfg_scale": CFG_SCALE, "matmul": "tf32" if args.dtype == "fp32" else "bf16 autocast",
                        "launch": "eager" if graphed is None else "CUDA graph replay (%d launches of this repo's kernels per step)"
