@@ -12,7 +12,7 @@
 // Mapping (third layout of this kernel; the first two put rows on lanes and paid for it in the dB/dC sums):
 //   * a lane owns TWO STATES of a PAIR OF ROWS: every recurrence value is a packed f32x2 (row 2p, row 2p+1), so the
 //     per-row scalars (delta, delta*u, dy) arrive as natural pairs from interleaved shared tiles and only B / C need a
-//     splat -- which the tile stores pre-duplicated;
+//     splat (a register move);
 //   * 8 lanes (16 states) form a row group that walks its 2 row pairs one after the other, so dB / dC of the 4 rows
 //     accumulate in registers and meet the other 15 groups of the CTA once per 4 steps through shared memory;
 //   * what has to cross lanes per step is only the two 16-state dot products (sum_n e A, sum_n g B): 8 packed values per
@@ -60,8 +60,8 @@ struct BwdSmem {
     float4 X[kMinis * kTileM];            // (delta r0, delta r1, delta*u r0, delta*u r1); later (ddelta r0, r1, du r0, r1)
     float4 Y[kMinis * kTileM];            // (dy r0, dy r1, D dy r0, D dy r1)
     float4 Z[kMinis * kTileM];            // (ln2 s' r0, ln2 s' r1, u s' r0, u s' r1) with s' = d softplus / d raw delta
-    float4 Bd[kSub][kLn];                 // (B_n0, B_n0, B_n0+1, B_n0+1) per lane
-    float4 Cd[kSub][kLn];
+    float2 Bd[kSub][kLn];                 // (B_n0, B_n0+1) per lane
+    float2 Cd[kSub][kLn];
     float4 hs[kPairs][kSub / kMini - 1][kLn];   // state at the start of mini-chunks 0..2: (n0 r0, n0 r1, n0+1 r0, n0+1 r1)
     float st[kGroups * kStGroup];         // transposing tile of the row groups; reused for the dB/dC hand-over
 };
@@ -132,9 +132,9 @@ __global__ void __launch_bounds__(kT, kMinCtas) scan_bwd_kernel(const ScanBwdArg
     }
 
     // one forward step of this lane's 2 states x 2 rows; leaves the decays in dec
-    auto fwd_step = [&](const float4 v, const float4 Bv, int q, float2 (&h)[2], float2 (&dec)[2]) {
+    auto fwd_step = [&](const float4 v, const float2 Bv, int q, float2 (&h)[2], float2 (&dec)[2]) {
         const float2 dlt = make_float2(v.x, v.y), dtu = make_float2(v.z, v.w);
-        const float2 Bs[2] = {make_float2(Bv.x, Bv.y), make_float2(Bv.z, Bv.w)};
+        const float2 Bs[2] = {splat2(Bv.x), splat2(Bv.y)};
 #pragma unroll
         for (int si = 0; si < 2; ++si) {
             const float2 t = mul2(dlt, A2[q][si]);
@@ -228,7 +228,8 @@ __global__ void __launch_bounds__(kT, kMinCtas) scan_bwd_kernel(const ScanBwdArg
                 s.Z[e] = make_float4(sk[0][i], sk[1][i], su[0][i], su[1][i]);
             }
         }
-        // B / C tiles, duplicated so that a lane's 16-byte load is two ready-made splats
+        // B / C tiles [step][state]: a lane's 8-byte load is its two states (the splats over the row pair are register moves:
+        // the LSU pipe is the busy one, the issue slots are not)
         for (int idx = tid; idx < 2 * 16 * VPR; idx += kT) {
             const int which = idx / (16 * VPR), rem = idx % (16 * VPR);
             const int n = rem % 16, col = (rem / 16) * VEC;
@@ -244,10 +245,9 @@ __global__ void __launch_bounds__(kT, kMinCtas) scan_bwd_kernel(const ScanBwdArg
                     for (int i = 0; i < VEC; ++i) bv[i] = (l0 + col + i < L) ? Io<T>::ld(src + i) : 0.f;
                 }
             }
-            float4 *tile = which ? &s.Cd[0][0] : &s.Bd[0][0];
+            float *tile = which ? &s.Cd[0][0].x : &s.Bd[0][0].x;
 #pragma unroll
-            for (int i = 0; i < VEC; ++i)
-                reinterpret_cast<float2 *>(tile + (col + i) * kLn)[n] = make_float2(bv[i], bv[i]);
+            for (int i = 0; i < VEC; ++i) tile[(col + i) * 2 * kLn + n] = bv[i];
         }
         __syncthreads();
 
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(kT, kMinCtas) scan_bwd_kernel(const ScanBwdArg
                 for (int q = 0; q < 2; ++q) s.hs[grp * 2 + q][m][ln] = make_float4(h[q][0].x, h[q][0].y, h[q][1].x, h[q][1].y);
 #pragma unroll
                 for (int i = 0; i < kMini; ++i) {
-                    const float4 Bv = s.Bd[m * kMini + i][ln];           // one load serves both row pairs
+                    const float2 Bv = s.Bd[m * kMini + i][ln];           // one load serves both row pairs
 #pragma unroll
                     for (int q = 0; q < 2; ++q) fwd_step(s.X[tile_at(m, grp * 2 + q, i)], Bv, q, h[q], dtmp);
                 }
@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(kT, kMinCtas) scan_bwd_kernel(const ScanBwdArg
 #pragma unroll 1
         for (int m = kMinis - 1; m >= 0; --m) {
             float accB[kMini][2], accC[kMini][2];               // dB / dC of this group's 4 rows
-            float4 Bm[kMini], Cm[kMini];                        // B / C of the 4 steps: loaded once, used by both row pairs
+            float2 Bm[kMini], Cm[kMini];                        // B / C of the 4 steps: loaded once, used by both row pairs
 #pragma unroll
             for (int i = 0; i < kMini; ++i) {
                 accB[i][0] = accB[i][1] = accC[i][0] = accC[i][1] = 0.f;
@@ -323,8 +323,8 @@ __global__ void __launch_bounds__(kT, kMinCtas) scan_bwd_kernel(const ScanBwdArg
                 for (int i = kMini - 1; i >= 0; --i) {
                     const float2 dyv = *reinterpret_cast<const float2 *>(&s.Y[e0 + i]);
                     const float2 dlt = make_float2(xv[i].x, xv[i].y), dtu = make_float2(xv[i].z, xv[i].w);
-                    const float2 Bs[2] = {make_float2(Bm[i].x, Bm[i].y), make_float2(Bm[i].z, Bm[i].w)};
-                    const float2 Cs[2] = {make_float2(Cm[i].x, Cm[i].y), make_float2(Cm[i].z, Cm[i].w)};
+                    const float2 Bs[2] = {splat2(Bm[i].x), splat2(Bm[i].y)};
+                    const float2 Cs[2] = {splat2(Cm[i].x), splat2(Cm[i].y)};
                     float2 P = make_float2(0.f, 0.f), Q = make_float2(0.f, 0.f);
 #pragma unroll
                     for (int si = 0; si < 2; ++si) {
