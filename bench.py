@@ -339,6 +339,16 @@ def run_b200(args, rank, local_rank, world):
     barrier()
     ms_e2e = e0.elapsed_time(e1) / args.steps
 
+    if args.profile and rank == 0:
+        from torch.profiler import ProfilerActivity, profile
+        xe = x0.clone()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for i in range(2):
+                xe = eager_step(xe, i)
+            torch.cuda.synchronize()
+        with open(args.profile, "w") as f:
+            f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=100))
+
     if world > 1:
         tt = torch.tensor([ms, ms_e2e, scan_ms, fast_ms or 0.0], device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -419,6 +429,8 @@ def main():
     ap.add_argument("--latents", type=int, default=TOTAL_LATENTS)
     ap.add_argument("--px", type=int, default=256, choices=[256, 512], help="image size: 256 (L=256 tokens) or 512 (L=1024, configs[3])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", default=None,
+                    help="also write a torch.profiler kernel table of two eager steps to this file (after all timing)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying a CUDA graph")
     ap.add_argument("--init-form-fastpath", action="store_true",
                     help="let the scan use its one-exp-per-step path for arithmetic-progression A.  The random-init benchmark "
