@@ -83,7 +83,7 @@ template <> DEV void st4<__half>(__half *p, const float (&v)[4]) {
 
 // kVec4: every thread moves 4 consecutive channels per access (needs 16-byte aligned fp32 rows / 8-byte aligned 16-bit rows)
 template <typename T, bool kInverse, bool kVec4>
-__global__ void __launch_bounds__(kWaveThreads) wavelet_kernel(const WaveArgs a) {
+__global__ void __launch_bounds__(kWaveThreads, 3) wavelet_kernel(const WaveArgs a) {
     extern __shared__ __align__(16) float tile[];   // [16][C + 4] fp32
     constexpr int CH = kVec4 ? 4 : 1;
     const int C = a.channels, pitch = C + 4, Cq = C / 16;
@@ -135,14 +135,18 @@ __global__ void __launch_bounds__(kWaveThreads) wavelet_kernel(const WaveArgs a)
             stc(dst + (int64_t)seq_of(t16) * a.d_ts + c, v);
         }
     } else {
-        for (int idx = threadIdx.x * CH; idx < 16 * C; idx += blockDim.x * CH) {
-            const int t16 = idx / C, c = idx % C;
-            float v[CH];
-            ldc(src + (int64_t)seq_of(t16) * a.s_ts + c, v);
-            if constexpr (kVec4) {
-                *reinterpret_cast<float4 *>(&tile[t16 * pitch + c]) = make_float4(v[0], v[1], v[2], v[3]);
-            } else {
-                tile[t16 * pitch + c] = v[0];
+        // all 16 token rows of a channel group are requested before the first one is parked (16 loads in flight per thread)
+        for (int c0 = threadIdx.x * CH; c0 < C; c0 += blockDim.x * CH) {
+            float v[16][CH];
+#pragma unroll
+            for (int t16 = 0; t16 < 16; ++t16) ldc(src + (int64_t)seq_of(t16) * a.s_ts + c0, v[t16]);
+#pragma unroll
+            for (int t16 = 0; t16 < 16; ++t16) {
+                if constexpr (kVec4) {
+                    *reinterpret_cast<float4 *>(&tile[t16 * pitch + c0]) = make_float4(v[t16][0], v[t16][1], v[t16][2], v[t16][3]);
+                } else {
+                    tile[t16 * pitch + c0] = v[t16][0];
+                }
             }
         }
         __syncthreads();
@@ -162,6 +166,8 @@ __global__ void __launch_bounds__(kWaveThreads) wavelet_kernel(const WaveArgs a)
                 for (int j1 = 0; j1 < 4; ++j1)
 #pragma unroll
                     for (int j2 = 0; j2 < 4; ++j2) px[patch_pixel(j2, j1)][i] = tmp[4 * j1 + j2] * a.scale;
+                // keep the four channels' gathers from being hoisted together (136 registers -> 3 CTAs/SM otherwise)
+                asm volatile("" ::: "memory");
             }
 #pragma unroll
             for (int t = 0; t < 16; ++t) stc(dst + (int64_t)token_of(t) * a.d_ts + c0, px[t]);

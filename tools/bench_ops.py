@@ -109,6 +109,10 @@ def main():
         med, best = timeit(lambda: wavelet_packet(x, pos), flush=flush)
         rows.append(dict(op="wavelet_fwd", dtype=str(dtype), R=512, D=512, L=256, ms=med, ms_best=best, gbs=by_w / med / 1e6,
                          frac=by_w / med / 1e6 / pk))
+        from dimsum_b200 import wavelet_packet_inverse
+        med, best = timeit(lambda: wavelet_packet_inverse(x, pos), flush=flush)
+        rows.append(dict(op="wavelet_inv", dtype=str(dtype), R=512, D=512, L=256, ms=med, ms_best=best, gbs=by_w / med / 1e6,
+                         frac=by_w / med / 1e6 / pk))
     for r in rows:
         print(f"{r['op']:20s} {r['dtype']:15s} R={r['R']:4d} D={r['D']:5d} L={r['L']:5d}  {r['ms']:8.3f} ms (best {r['ms_best']:.3f})"
               f"  {r['gbs']:8.1f} GB/s  {100 * r['frac']:5.1f}% of measured peak {pk:.0f}")
