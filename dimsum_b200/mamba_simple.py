@@ -5,10 +5,13 @@ unchanged (`in_proj`, `conv1d`, `x_proj`, `dt_proj`, `cond_proj`, `A_log`, `D`, 
 `zigzag_paths[_reverse]` buffers when scan_type != "none").
 
 What is different is how the token order is applied.  The reference gathers `xz` (batch, 2*d_inner, L) and the output
-(batch, L, d_model) into permuted copies (mamba_simple.py:634,657).  Here the conv reads x through the table, the scan
-reads z and writes its gated output through the table, so out_proj already sees natural token order and no permuted
-copy is ever materialised.  `forward(..., order=perm)` lets the enclosing block pass the implicit
-transpose / flip orders of the released configuration through the same mechanism.
+(batch, L, d_model) into permuted copies (mamba_simple.py:634,657).  Here there are three routes, all without a permuted
+copy of xz: (1) inside the DiM blocks the order -- implicit transpose / flip or this layer's zigma / sweep / jpeg table --
+is folded into the row index of the modulate and gated-residual kernels that surround the mixer, so the mixer itself runs
+gather-free (`pre_ordered=True`); (2) a stand-alone call gathers the (batch, L, d_model) token rows before in_proj and
+after out_proj (coalesced 2 KB rows of a tensor 4x smaller than xz); (3) `in_kernel_gather=True` makes the conv read x and
+the scan read z / write its output through the table inside the kernels (`perm` of the C ABI) -- kept for the API, but a
+channel-major 4-byte gather is 3x slower than route (2) (profiles/r1_ops_bench.md).
 """
 import math
 import os
@@ -71,7 +74,9 @@ class Mamba(nn.Module):
         self._order_cache = {}
         self._arith_key, self._arith_flag = None, False
 
-    def _table_order(self, device):
+    def table_order(self, device):
+        """This layer's scan table (zigma / sweep / jpeg scan types, models_dim.py:1640-1658) as an int32 CUDA index: sequence
+        position k reads token table[k]; None for scan_type "none"."""
         if not self.scan_type.startswith(("zigma", "sweep", "jpeg")):
             return None
         key = (self.layer_idx, device)
@@ -79,23 +84,42 @@ class Mamba(nn.Module):
             self._order_cache[key] = self.zigzag_paths[self.layer_idx].to(device=device, dtype=torch.int32).contiguous()
         return self._order_cache[key]
 
-    def forward(self, hidden_states, cond_emb=None, inference_params=None, order=None):
-        """hidden_states (B, L, D) -> (B, L, D).  `order`: optional int32 (L,) CUDA table; the conv + scan then run over
-        tokens order[0], order[1], ... while input and output stay in natural token order."""
+    _table_order = table_order
+
+    @staticmethod
+    def inverse_order(order):
+        """Inverse permutation, computed on the device (no host round trip, CUDA-graph safe)."""
+        inv = torch.empty_like(order)
+        inv[order.long()] = torch.arange(order.numel(), device=order.device, dtype=order.dtype)
+        return inv
+
+    def forward(self, hidden_states, cond_emb=None, inference_params=None, order=None, pre_ordered=False,
+                in_kernel_gather=False):
+        """hidden_states (B, L, D) -> (B, L, D).
+
+        `order`: optional int32 (L,) CUDA table applied in front of this layer's own scan table; the conv + scan run over
+        tokens order[0], order[1], ... while input and output stay in natural token order.
+        `pre_ordered`: the caller has already put the rows in this layer's sequence order (and will undo it) -- what the
+        DiM blocks do, folding the order into their modulate / gated-residual kernels at no cost.
+        `in_kernel_gather`: read z / write the output through the table inside the conv and scan kernels (channel-major
+        4-byte gathers; measured 3x slower than the two coalesced row gathers used by default, see profiles/)."""
         if inference_params is not None:
             raise NotImplementedError("autoregressive decode (inference_params) is outside the DiMSUM hot path")
-        table = self._table_order(hidden_states.device)
+        if pre_ordered:
+            return self._mix(hidden_states, None)
+        table = self.table_order(hidden_states.device)
         if table is not None and order is not None:
             order = order[table.long()].contiguous()
         elif table is not None:
             order = table
-        if order is not None and torch.is_grad_enabled():
-            # training through an explicit order: gather token rows (coalesced), run the plain composite, gather back
-            from .scanning_orders import permute_tokens
-            inv = torch.empty_like(order)                       # inverse permutation on the device: no host round trip
-            inv[order.long()] = torch.arange(order.numel(), device=order.device, dtype=order.dtype)
-            return permute_tokens(self._mix(permute_tokens(hidden_states.contiguous(), order, inv), None), inv, order)
-        return self._mix(hidden_states, order)
+        if order is None:
+            return self._mix(hidden_states, None)
+        if in_kernel_gather and not torch.is_grad_enabled():
+            return self._mix(hidden_states, order)
+        # gather token rows (coalesced 2 KB rows of a tensor 4x smaller than xz), run the plain composite, gather back
+        from .scanning_orders import permute_tokens
+        inv = self.inverse_order(order)
+        return permute_tokens(self._mix(permute_tokens(hidden_states.contiguous(), order, inv), None), inv, order)
 
     def _a_is_arithmetic(self, A):
         """True when every row of A is (n+1) * A[:, 0] -- the S4D-real init above, and any state that keeps it.  Checked on

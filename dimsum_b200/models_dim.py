@@ -192,6 +192,20 @@ class CrossAttentionFusion(nn.Module):
         return self.proj(torch.cat((x12, x21), dim=-1))
 
 
+def _block_order(mixer, order, inv, device):
+    """Sequence order a block has to present to its mixer: the block's implicit order composed with the mixer's scan table
+    (sequence position k reads token order[table[k]]), and its inverse; (None, None) when there is nothing to reorder."""
+    table = mixer.table_order(device) if hasattr(mixer, "table_order") else None
+    if table is None:
+        return order, inv
+    key = (device, None if order is None else order.data_ptr())
+    cache = mixer.__dict__.setdefault("_block_order_cache", {})
+    if key not in cache:
+        total = table if order is None else order[table.long()].contiguous()
+        cache[key] = (total, mixer.inverse_order(total))
+    return cache[key]
+
+
 def _order_buffer(table):
     return torch.from_numpy(np.ascontiguousarray(table).astype(np.int32))
 
@@ -213,9 +227,11 @@ class DiMBlockRaw(nn.Module):
     def forward(self, x, c):
         shift, scale, gate = self.adaLN_modulation(c).chunk(3, dim=1)
         if _fused_ok(x):
-            # the scan order rides on the row index of the two glue kernels: no permuted copy, no extra pass
-            m = self.mixer(_mod(x, shift, scale, self._order), c)
-            return _gated(x, gate, m, self._inv, feeds_gemm=True)
+            # the scan order (implicit transpose / flip, or the mixer's zigma / sweep / jpeg table) rides on the row index
+            # of the two glue kernels: no permuted copy, no extra pass, and the mixer runs gather-free
+            order, inv = _block_order(self.mixer, self._order, self._inv, x.device)
+            m = self.mixer(_mod(x, shift, scale, order), c, pre_ordered=True)
+            return _gated(x, gate, m, inv, feeds_gemm=True)
         return x + gate.unsqueeze(1) * self.mixer(modulate(x, shift, scale), c, order=self._order)
 
 
@@ -242,7 +258,11 @@ class WaveDiMBlock(nn.Module):
     def forward(self, x, c):
         h = wavelet_packet(x, self._pos)                                 # _dwt_fast + local_scan
         shift, scale, gate = self.adaLN_modulation(c).chunk(3, dim=1)
-        h = _gated(h, gate, self.mixer(_mod(h, shift, scale), c), feeds_gemm=True)
+        if _fused_ok(h):
+            order, inv = _block_order(self.mixer, None, None, h.device)      # the mixer's own table, if its scan type has one
+            h = _gated(h, gate, self.mixer(_mod(h, shift, scale, order), c, pre_ordered=True), inv, feeds_gemm=True)
+        else:
+            h = _gated(h, gate, self.mixer(_mod(h, shift, scale), c), feeds_gemm=True)
         return wavelet_packet_inverse(h, self._pos)                      # local_reverse + _idwt_fast
 
 

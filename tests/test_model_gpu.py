@@ -61,9 +61,35 @@ def test_scan_table_orders_match_explicit_gathers():
     plain.load_state_dict({k: v for k, v in mixer.state_dict().items() if "zigzag" not in k})
     h = torch.randn(3, grid * grid, d_model, device="cuda")
     with torch.no_grad():
-        got = mixer(h)
         want = plain(h[:, fwd[5].cuda()])[:, rev[5].cuda()]
+        got = mixer(h)                                              # default: two coalesced row gathers around the mixer
+        assert rel_err(got, want) <= 1e-5
+        got = mixer(h, in_kernel_gather=True)                       # conv / scan reading and writing through the table
+        assert rel_err(got, want) <= 1e-5
+        table = mixer.table_order(h.device)
+        got = mixer(h[:, table.long()], pre_ordered=True)[:, mixer.inverse_order(table).long()]    # what the DiM blocks do
+        assert rel_err(got, want) <= 1e-5
+    got = mixer(h.clone().requires_grad_(True))                     # autograd route
     assert rel_err(got, want) <= 1e-5
+
+
+def test_model_with_table_scan_type_folds_the_order_into_the_glue_kernels():
+    """scan_type='zigma_8': the inference path (table folded into modulate / gated residual, mixer gather-free) equals the
+    recorded path (explicit token gathers around the mixer)."""
+    from dimsum_b200.models_dim import DiM
+    torch.manual_seed(0)
+    model = DiM(img_resolution=32, depth=4, hidden_size=128, scan_type="zigma_8", num_classes=10, use_attn_every_k_layers=2).cuda().eval()
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if "adaLN_modulation" in n or n.startswith("final_layer.linear"):
+                p.normal_(0, 0.05)
+    x = torch.randn(3, 4, 32, 32, device="cuda")
+    t = torch.rand(3, device="cuda")
+    y = torch.randint(0, 10, (3,), device="cuda")
+    with torch.no_grad():
+        fast = model(x, t, y)
+    slow = model(x, t, y).detach()              # grad mode on: PyTorch glue ops + explicit gathers
+    assert rel_err(fast, slow) <= 2e-5
 
 
 def test_fixed_seed_cfg_sampling_matches_oracle_sampler():

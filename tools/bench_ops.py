@@ -113,6 +113,54 @@ def main():
         med, best = timeit(lambda: wavelet_packet_inverse(x, pos), flush=flush)
         rows.append(dict(op="wavelet_inv", dtype=str(dtype), R=512, D=512, L=256, ms=med, ms_best=best, gbs=by_w / med / 1e6,
                          frac=by_w / med / 1e6 / pk))
+        # the order-carrying and glue kernels at the model's shapes (512 rows x 256 tokens, 512 / 1024 / 4096 channels)
+        from dimsum_b200 import fused
+        R, L, C = 512, 256, 1024
+        g = torch.Generator(device="cuda").manual_seed(1)
+        order = so.as_index(so.implicit_order(16, True, True), "cuda")
+        inv = so.as_index(so.reverse_permut_np(so.implicit_order(16, True, True)), "cuda")
+        h = torch.randn(R, L, C, generator=g, device="cuda")                      # fp32 residual stream
+        xh = h[:, :, :C // 2].to(dtype) if dtype != torch.float32 else h[:, :, :C // 2]
+        ada = (0.1 * torch.randn(R, 3 * C, generator=g, device="cuda")).to(dtype)
+        sh, sc, gt = ada.chunk(3, dim=1)
+        sh2, sc2, gt2 = (t[:, :C // 2] for t in (sh, sc, gt))
+        m = torch.randn(R, L, C // 2, generator=g, device="cuda").to(dtype)
+
+        def add(op, fn, nbytes, Cc):
+            med, best = timeit(fn, flush=flush)
+            rows.append(dict(op=op, dtype=str(dtype), R=R, D=Cc, L=L, ms=med, ms_best=best, gbs=nbytes / med / 1e6,
+                             frac=nbytes / med / 1e6 / pk))
+
+        n_half = R * L * (C // 2)
+        add("modulate_order", lambda: fused.modulate(xh, sh2, sc2, order), 2 * s * n_half, C // 2)
+        add("gate_residual_order", lambda: fused.gate_residual(xh, gt2, m, inv), 3 * s * n_half, C // 2)
+        add("token_gather", lambda: so.token_gather(m, order), 2 * s * n_half, C // 2)
+        xo = torch.randn(R, L, C, generator=g, device="cuda").to(dtype)
+        w = torch.ones(C, device="cuda")
+        add("add_rmsnorm", lambda: fused.add_rmsnorm(xo, h, w, 1e-5), (s + 4 + 4 + s) * R * L * C, C)
+        add("norm_modulate", lambda: fused.norm_modulate(xo, h, w, 1e-5, sh, sc, want_residual=True), (s + 4 + 4 + s) * R * L * C, C)
+        x12 = torch.randn(R * L, 8 * C, generator=g, device="cuda").to(dtype)
+        add("gelu_mul", lambda: fused.gelu_mul(x12), 3 * s * R * L * 4 * C, 4 * C)
+        del x12, xo, h, m
+        # conv / scan read through a jpeg table (scan_type="jpeg_8" of the reference): the gather variants
+        Rr, Dd = 256, 1024
+        perm = so.as_index(so.SCAN_ZOO["jpeg"](16)[1], "cuda")
+        xz = torch.randn(Rr, 2 * Dd, L, generator=g, device="cuda").to(dtype)
+        wc, cb = torch.randn(Dd, 4, generator=g, device="cuda"), torch.randn(Dd, generator=g, device="cuda")
+        med, best = timeit(lambda: causal_conv1d_cuda.causal_conv1d_fwd(xz[:, :Dd], wc, cb, True, perm=perm), flush=flush)
+        by = 2 * s * Rr * Dd * L
+        rows.append(dict(op="conv_fwd_perm", dtype=str(dtype), R=Rr, D=Dd, L=L, ms=med, ms_best=best, gbs=by / med / 1e6, frac=by / med / 1e6 / pk))
+        u = causal_conv1d_cuda.causal_conv1d_fwd(xz[:, :Dd], wc, cb, True, perm=perm)
+        delta = (0.5 * torch.rand(Dd, Rr, L, generator=g, device="cuda")).to(dtype).transpose(0, 1)
+        A = -0.5 * torch.rand(Dd, N, generator=g, device="cuda")
+        Bm = torch.randn(Rr, 1, N, L, generator=g, device="cuda").to(dtype)
+        Cm = torch.randn(Rr, 1, N, L, generator=g, device="cuda").to(dtype)
+        Dv, bias = torch.randn(Dd, generator=g, device="cuda"), 0.5 * torch.rand(Dd, generator=g, device="cuda")
+        by = s * (4 * Rr * Dd * L + 2 * Rr * N * L)
+        med, best = timeit(lambda: selective_scan_cuda.fwd(u, delta, A, Bm, Cm, Dv, xz[:, Dd:], bias, True, need_out=False,
+                                                           need_x=False, perm=perm), flush=flush)
+        rows.append(dict(op="scan_fwd_infer_perm", dtype=str(dtype), R=Rr, D=Dd, L=L, ms=med, ms_best=best, gbs=by / med / 1e6, frac=by / med / 1e6 / pk))
+        del xz, u, delta, Bm, Cm
     for r in rows:
         print(f"{r['op']:20s} {r['dtype']:15s} R={r['R']:4d} D={r['D']:5d} L={r['L']:5d}  {r['ms']:8.3f} ms (best {r['ms_best']:.3f})"
               f"  {r['gbs']:8.1f} GB/s  {100 * r['frac']:5.1f}% of measured peak {pk:.0f}")
