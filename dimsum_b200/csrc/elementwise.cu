@@ -85,10 +85,10 @@ DEV void st_rt(void *base, int dtype, int64_t idx, const float (&v)[VEC]) {
 
 // residual add + RMSNorm / LayerNorm (+ adaLN modulate): one warp per row, the row lives in registers between the
 // passes (channels <= 32 lanes * 8 * VEC: 1024 fp32, 2048 16-bit)
-template <typename T, bool kLayerNorm>
+// kMaxIter = 16-byte vectors per lane (1, 2, 4 or 8): sized to the row so that no predicated-off iterations are issued
+template <typename T, bool kLayerNorm, int kMaxIter>
 __global__ void __launch_bounds__(256) norm_kernel(const dimsum_norm_modulate_params p) {
     constexpr int VEC = Io<T>::kVec;
-    constexpr int kMaxIter = 8;
     const int warp = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
     if (warp >= p.rows) return;
@@ -183,13 +183,20 @@ int run_norm(const dimsum_norm_modulate_params *p, cudaStream_t stream, const ch
                    DIMSUM_ERR_UNSUPPORTED, "%s: rows must be 16-byte aligned", who);
     if (p->rows == 0) return DIMSUM_OK;
     const unsigned blocks = (unsigned)((p->rows * 32 + 255) / 256);
-#define NK(T)                                                                  \
-    if (p->norm_kind == 1) norm_kernel<T, true><<<blocks, 256, 0, stream>>>(*p); \
-    else norm_kernel<T, false><<<blocks, 256, 0, stream>>>(*p);
+    const int per_lane = (int)((p->channels / vec + 31) / 32);
+#define NKI(T, I)                                                                      \
+    if (p->norm_kind == 1) norm_kernel<T, true, I><<<blocks, 256, 0, stream>>>(*p);    \
+    else norm_kernel<T, false, I><<<blocks, 256, 0, stream>>>(*p);
+#define NK(T)                                     \
+    if (per_lane <= 1) { NKI(T, 1) }              \
+    else if (per_lane <= 2) { NKI(T, 2) }         \
+    else if (per_lane <= 4) { NKI(T, 4) }         \
+    else { NKI(T, 8) }
     if (p->x_dtype == DIMSUM_F32) { NK(float) }
     else if (p->x_dtype == DIMSUM_BF16) { NK(__nv_bfloat16) }
     else { NK(__half) }
 #undef NK
+#undef NKI
     return check_launch(who);
 }
 
