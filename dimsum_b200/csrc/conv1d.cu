@@ -30,61 +30,62 @@ DEV float load_w(const void *w, int dtype, int64_t idx) {
 // ---------------------------------------------------------------------------------------------- forward
 // kNV consecutive 16-byte vectors per thread (2 when the row length allows it: twice the bytes in flight per thread,
 // which is what a pure streaming kernel at full occupancy needs to cover HBM latency on B200).
-template <typename T, int kNV>
+// Indexing is 32-bit inside a batch row (blockIdx.y walks the batch): the 64-bit div / mod chain of a flat index cost more
+// instructions than the convolution itself and made the 16-bit variant issue-bound.
+template <typename T, int kNV, bool kSilu>
 __global__ void __launch_bounds__(256) conv_fwd_vec_kernel(const ConvArgs a) {
     constexpr int VEC = Io<T>::kVec;
     constexpr int W = kNV * VEC;                      // elements per thread
-    const int tpr = a.seqlen / W;                     // threads per row
-    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t total = (int64_t)a.batch * a.dim * tpr;
-    const bool active = gid < total;
+    const unsigned tpr = (unsigned)a.seqlen / W;      // threads per row
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = idx < (unsigned)a.dim * tpr;
     const int lane = threadIdx.x & 31;
-    const int v = active ? (int)(gid % tpr) : 0;
-    const int64_t row = active ? gid / tpr : 0;
-    const int d = (int)(row % a.dim);
-    const int b = (int)(row / a.dim);
-    const T *xr = reinterpret_cast<const T *>(a.x) + b * a.x_bs + d * a.x_ds + v * W;
-
-    float xv[W + kMaxW - 1];   // [0..2] halo, [3..] own elements
-#pragma unroll
-    for (int i = 0; i < W + kMaxW - 1; ++i) xv[i] = 0.f;
-    if (active) {
-#pragma unroll
-        for (int j = 0; j < kNV; ++j) Io<T>::ldv(xr + j * VEC, reinterpret_cast<float(&)[VEC]>(xv[kMaxW - 1 + j * VEC]));
-    }
-    // halo: last 3 elements of the previous thread of the same row
-    const float h0 = __shfl_up_sync(0xffffffffu, xv[W + kMaxW - 4], 1);
-    const float h1 = __shfl_up_sync(0xffffffffu, xv[W + kMaxW - 3], 1);
-    const float h2 = __shfl_up_sync(0xffffffffu, xv[W + kMaxW - 2], 1);
-    if (active && v > 0) {
-        if (lane > 0) {
-            xv[0] = h0; xv[1] = h1; xv[2] = h2;
-        } else {
-            xv[0] = Io<T>::ld(xr - 3);
-            xv[1] = Io<T>::ld(xr - 2);
-            xv[2] = Io<T>::ld(xr - 1);
-        }
-    }
-    if (!active) return;
+    const unsigned d = active ? idx / tpr : 0u;
+    const unsigned v = active ? idx - d * tpr : 0u;
     float w[kMaxW];
 #pragma unroll
     for (int i = 0; i < kMaxW; ++i) {   // right-align the taps: w[3] multiplies x[l]
         const int wi = i - (kMaxW - a.width);
-        w[i] = wi >= 0 ? load_w(a.weight, a.w_dtype, d * a.w_ds + wi * a.w_ws) : 0.f;
+        w[i] = wi >= 0 ? load_w(a.weight, a.w_dtype, (int64_t)d * a.w_ds + wi * a.w_ws) : 0.f;
     }
     const float bias = a.bias != nullptr ? load_w(a.bias, a.w_dtype, d) : 0.f;
-    T *orow = reinterpret_cast<T *>(a.out) + b * a.o_bs + d * a.o_ds + v * W;
+    for (int b = blockIdx.y; b < a.batch; b += gridDim.y) {
+        const T *xr = reinterpret_cast<const T *>(a.x) + (int64_t)b * a.x_bs + (int64_t)d * a.x_ds + v * W;
+        float xv[W + kMaxW - 1];   // [0..2] halo, [3..] own elements
 #pragma unroll
-    for (int j = 0; j < kNV; ++j) {
-        float ov[VEC];
+        for (int i = 0; i < W + kMaxW - 1; ++i) xv[i] = 0.f;
+        if (active) {
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-            float acc = bias;
-#pragma unroll
-            for (int k = 0; k < kMaxW; ++k) acc = fmaf(w[k], xv[j * VEC + i + k], acc);
-            ov[i] = a.silu ? silu_t<sizeof(T) == 2>(acc) : acc;
+            for (int j = 0; j < kNV; ++j) Io<T>::ldv(xr + j * VEC, reinterpret_cast<float(&)[VEC]>(xv[kMaxW - 1 + j * VEC]));
         }
-        Io<T>::stv(orow + j * VEC, ov);
+        // halo: last 3 elements of the previous thread of the same row
+        const float h0 = __shfl_up_sync(0xffffffffu, xv[W + kMaxW - 4], 1);
+        const float h1 = __shfl_up_sync(0xffffffffu, xv[W + kMaxW - 3], 1);
+        const float h2 = __shfl_up_sync(0xffffffffu, xv[W + kMaxW - 2], 1);
+        if (active && v > 0) {
+            if (lane > 0) {
+                xv[0] = h0; xv[1] = h1; xv[2] = h2;
+            } else {
+                xv[0] = Io<T>::ld(xr - 3);
+                xv[1] = Io<T>::ld(xr - 2);
+                xv[2] = Io<T>::ld(xr - 1);
+            }
+        }
+        if (active) {
+            T *orow = reinterpret_cast<T *>(a.out) + (int64_t)b * a.o_bs + (int64_t)d * a.o_ds + v * W;
+#pragma unroll
+            for (int j = 0; j < kNV; ++j) {
+                float ov[VEC];
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) {
+                    float acc = bias;
+#pragma unroll
+                    for (int k = 0; k < kMaxW; ++k) acc = fmaf(w[k], xv[j * VEC + i + k], acc);
+                    ov[i] = kSilu ? silu_t<sizeof(T) == 2>(acc) : acc;
+                }
+                Io<T>::stv(orow + j * VEC, ov);
+            }
+        }
     }
 }
 
@@ -95,15 +96,13 @@ constexpr int kGW = 8;
 
 template <typename T>
 __global__ void __launch_bounds__(256) conv_fwd_scalar_kernel(const ConvArgs a) {
-    const int tpr = (a.seqlen + kGW - 1) / kGW;                  // threads per row
-    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t total = (int64_t)a.batch * a.dim * tpr;
-    if (gid >= total) return;
-    const int l0 = (int)(gid % tpr) * kGW;
-    const int64_t row = gid / tpr;
-    const int d = (int)(row % a.dim);
-    const int b = (int)(row / a.dim);
-    const T *xr = reinterpret_cast<const T *>(a.x) + b * a.x_bs + d * a.x_ds;
+    const unsigned tpr = (unsigned)(a.seqlen + kGW - 1) / kGW;   // threads per row
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;  // 32-bit inside a batch row, blockIdx.y = batch
+    if (idx >= (unsigned)a.dim * tpr) return;
+    const unsigned d = idx / tpr;
+    const int l0 = (int)(idx - d * tpr) * kGW;
+    const int64_t b = blockIdx.y;
+    const T *xr = reinterpret_cast<const T *>(a.x) + b * a.x_bs + (int64_t)d * a.x_ds;
     float xs[kGW + kMaxW - 1];
 #pragma unroll
     for (int i = 0; i < kGW + kMaxW - 1; ++i) {
@@ -116,7 +115,7 @@ __global__ void __launch_bounds__(256) conv_fwd_scalar_kernel(const ConvArgs a) 
 #pragma unroll
     for (int i = 0; i < kMaxW; ++i) {
         const int wi = i - (kMaxW - a.width);
-        w[i] = wi >= 0 ? load_w(a.weight, a.w_dtype, d * a.w_ds + wi * a.w_ws) : 0.f;
+        w[i] = wi >= 0 ? load_w(a.weight, a.w_dtype, (int64_t)d * a.w_ds + wi * a.w_ws) : 0.f;
     }
     const float bias = a.bias != nullptr ? load_w(a.bias, a.w_dtype, d) : 0.f;
     float ov[kGW];
@@ -127,7 +126,7 @@ __global__ void __launch_bounds__(256) conv_fwd_scalar_kernel(const ConvArgs a) 
         for (int k = 0; k < kMaxW; ++k) acc = fmaf(w[k], xs[i + k], acc);
         ov[i] = a.silu ? silu_t<sizeof(T) == 2>(acc) : acc;
     }
-    T *orow = reinterpret_cast<T *>(a.out) + b * a.o_bs + d * a.o_ds + l0;
+    T *orow = reinterpret_cast<T *>(a.out) + b * a.o_bs + (int64_t)d * a.o_ds + l0;
     if (a.out_vec_ok && l0 + kGW <= a.seqlen) {
 #pragma unroll
         for (int i = 0; i < kGW; i += Io<T>::kVec) Io<T>::stv(orow + i, reinterpret_cast<const float(&)[Io<T>::kVec]>(ov[i]));
@@ -307,16 +306,18 @@ template <typename T>
 int run_fwd(const ConvArgs &a, bool vec_ok, cudaStream_t stream) {
     if (vec_ok && a.perm == nullptr) {
         const int vpr = a.seqlen / Io<T>::kVec;
-        if (vpr % 2 == 0) {
-            const int64_t total = (int64_t)a.batch * a.dim * (vpr / 2);
-            conv_fwd_vec_kernel<T, 2><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(a);
-        } else {
-            const int64_t total = (int64_t)a.batch * a.dim * vpr;
-            conv_fwd_vec_kernel<T, 1><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(a);
-        }
+        const int nv = vpr % 2 == 0 ? 2 : 1;
+        const int64_t per_batch = (int64_t)a.dim * (vpr / nv);
+        DIMSUM_REQUIRE(per_batch < ((int64_t)1 << 31), DIMSUM_ERR_UNSUPPORTED, "causal_conv1d_fwd: dim * seqlen too large");
+        dim3 grid((unsigned)((per_batch + 255) / 256), (unsigned)min(a.batch, 65535));
+        auto go = [&](auto kern) { kern<<<grid, 256, 0, stream>>>(a); };
+        if (a.silu) { if (nv == 2) go(conv_fwd_vec_kernel<T, 2, true>); else go(conv_fwd_vec_kernel<T, 1, true>); }
+        else { if (nv == 2) go(conv_fwd_vec_kernel<T, 2, false>); else go(conv_fwd_vec_kernel<T, 1, false>); }
     } else {
-        const int64_t total = (int64_t)a.batch * a.dim * ((a.seqlen + kGW - 1) / kGW);
-        conv_fwd_scalar_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(a);
+        const int64_t per_batch = (int64_t)a.dim * ((a.seqlen + kGW - 1) / kGW);
+        DIMSUM_REQUIRE(per_batch < ((int64_t)1 << 31) && a.batch <= 65535, DIMSUM_ERR_UNSUPPORTED,
+                       "causal_conv1d_fwd: more than 65535 batch rows or dim * seqlen too large on the scalar / gather path");
+        conv_fwd_scalar_kernel<T><<<dim3((unsigned)((per_batch + 255) / 256), (unsigned)a.batch), 256, 0, stream>>>(a);
     }
     return check_launch("causal_conv1d_fwd");
 }

@@ -34,14 +34,13 @@ DEV void st8(void *base, int dtype, int64_t idx, const float (&v)[8]) {
 // one thread = 8 consecutive channels of one token; all loads are issued before the arithmetic
 template <bool kGate>
 __global__ void __launch_bounds__(256) rowwise_kernel(const dimsum_rowwise_params p) {
-    const int tpt = (int)(p.channels / 8);                    // threads per token row
-    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t total = p.batch * p.seqlen * tpt;
-    if (gid >= total) return;
-    const int v = (int)(gid % tpt);
-    const int64_t t = gid / tpt;
-    const int l = (int)(t % p.seqlen);
-    const int64_t b = t / p.seqlen;
+    // 32-bit indexing inside a batch row (blockIdx.y = batch): a flat 64-bit index costs three 64-bit divisions per thread
+    const unsigned tpt = (unsigned)(p.channels / 8);          // threads per token row
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (unsigned)p.seqlen * tpt) return;
+    const int l = (int)(idx / tpt);
+    const int v = (int)(idx - (unsigned)l * tpt);
+    const int64_t b = blockIdx.y;
     const int src_l = p.idx != nullptr ? p.idx[l] : l;
     const int c0 = v * 8;
     float a[8], q[8], r[8], o[8];
@@ -245,8 +244,10 @@ int rowwise_entry(const dimsum_rowwise_params *p, bool gate, void *stream_) {
     DIMSUM_REQUIRE(ok, DIMSUM_ERR_UNSUPPORTED, "%s: rows must be 16-byte aligned and channels a multiple of 8", who);
     DIMSUM_REQUIRE(p->dst != p->x || p->idx == nullptr || gate, DIMSUM_ERR_INVALID, "%s: in-place gather is not supported", who);
     if (p->batch == 0) return DIMSUM_OK;
-    const int64_t total = p->batch * p->seqlen * (p->channels / 8);
-    const unsigned blocks = (unsigned)((total + 255) / 256);
+    const int64_t per_batch = p->seqlen * (p->channels / 8);
+    DIMSUM_REQUIRE(per_batch < ((int64_t)1 << 31) && p->batch <= 65535, DIMSUM_ERR_UNSUPPORTED,
+                   "%s: more than 65535 batch rows or 2^31 vectors per batch row", who);
+    const dim3 blocks((unsigned)((per_batch + 255) / 256), (unsigned)p->batch);
     if (gate) rowwise_kernel<true><<<blocks, 256, 0, stream>>>(*p);
     else rowwise_kernel<false><<<blocks, 256, 0, stream>>>(*p);
     return check_launch(who);

@@ -177,13 +177,12 @@ __global__ void __launch_bounds__(kWaveThreads, 3) wavelet_kernel(const WaveArgs
 
 template <typename T>
 __global__ void __launch_bounds__(256) gather_kernel(const T *src, T *dst, const int32_t *index, int64_t s_bs, int64_t s_ts,
-                                                     int64_t d_bs, int64_t d_ts, int seqlen, int vecs_per_token, int64_t total) {
-    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= total) return;
-    const int v = (int)(gid % vecs_per_token);
-    const int64_t t = gid / vecs_per_token;
-    const int l = (int)(t % seqlen);
-    const int64_t b = t / seqlen;
+                                                     int64_t d_bs, int64_t d_ts, int seqlen, int vecs_per_token) {
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;        // 32-bit inside a batch row, blockIdx.y = batch
+    if (idx >= (unsigned)seqlen * (unsigned)vecs_per_token) return;
+    const unsigned l = idx / (unsigned)vecs_per_token;
+    const unsigned v = idx - l * (unsigned)vecs_per_token;
+    const int64_t b = blockIdx.y;
     const uint4 val = *reinterpret_cast<const uint4 *>(reinterpret_cast<const char *>(src + b * s_bs + (int64_t)index[l] * s_ts) + 16 * v);
     *reinterpret_cast<uint4 *>(reinterpret_cast<char *>(dst + b * d_bs + (int64_t)l * d_ts) + 16 * v) = val;
 }
@@ -258,17 +257,19 @@ extern "C" int dimsum_token_gather(const dimsum_gather_params *p, void *stream_)
     DIMSUM_REQUIRE(p->src != p->dst, DIMSUM_ERR_INVALID, "token_gather: in-place operation is not supported");
     if (p->batch == 0) return DIMSUM_OK;
     const int vpt = (int)(p->channels / vec);
-    const int64_t total = p->batch * p->seqlen * vpt;
-    const unsigned blocks = (unsigned)((total + 255) / 256);
+    const int64_t per_batch = p->seqlen * vpt;
+    DIMSUM_REQUIRE(per_batch < ((int64_t)1 << 31) && p->batch <= 65535, DIMSUM_ERR_UNSUPPORTED,
+                   "token_gather: more than 65535 batch rows or 2^31 vectors per batch row");
+    const dim3 blocks((unsigned)((per_batch + 255) / 256), (unsigned)p->batch);
     if (esz == 4) {
         gather_kernel<float><<<blocks, 256, 0, stream>>>(reinterpret_cast<const float *>(p->src), reinterpret_cast<float *>(p->dst),
                                                         p->index, p->src_batch_stride, p->src_token_stride, p->dst_batch_stride,
-                                                        p->dst_token_stride, (int)p->seqlen, vpt, total);
+                                                        p->dst_token_stride, (int)p->seqlen, vpt);
     } else {
         gather_kernel<uint16_t><<<blocks, 256, 0, stream>>>(reinterpret_cast<const uint16_t *>(p->src),
                                                            reinterpret_cast<uint16_t *>(p->dst), p->index, p->src_batch_stride,
                                                            p->src_token_stride, p->dst_batch_stride, p->dst_token_stride,
-                                                           (int)p->seqlen, vpt, total);
+                                                           (int)p->seqlen, vpt);
     }
     return check_launch("token_gather");
 }
