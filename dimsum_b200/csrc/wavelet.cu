@@ -123,16 +123,19 @@ __global__ void __launch_bounds__(kWaveThreads, 3) wavelet_kernel(const WaveArgs
             }
         }
         __syncthreads();
-        for (int idx = threadIdx.x * CH; idx < 16 * C; idx += blockDim.x * CH) {
-            const int t16 = idx / C, c = idx % C;
-            float v[CH];
-            if constexpr (kVec4) {
-                const float4 r = *reinterpret_cast<const float4 *>(&tile[t16 * pitch + c]);
-                v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w;
-            } else {
-                v[0] = tile[t16 * pitch + c];
+        // copy-out: a thread keeps its channel group and walks the 16 token rows (no div / mod, 16 independent LDS + STG)
+        for (int c0 = threadIdx.x * CH; c0 < C; c0 += blockDim.x * CH) {
+#pragma unroll
+            for (int t16 = 0; t16 < 16; ++t16) {
+                float v[CH];
+                if constexpr (kVec4) {
+                    const float4 r = *reinterpret_cast<const float4 *>(&tile[t16 * pitch + c0]);
+                    v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w;
+                } else {
+                    v[0] = tile[t16 * pitch + c0];
+                }
+                stc(dst + (int64_t)seq_of(t16) * a.d_ts + c0, v);
             }
-            stc(dst + (int64_t)seq_of(t16) * a.d_ts + c, v);
         }
     } else {
         // all 16 token rows of a channel group are requested before the first one is parked (16 loads in flight per thread)
