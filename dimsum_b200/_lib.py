@@ -114,6 +114,8 @@ RowwiseParams = STRUCTS["dimsum_rowwise_params"]
 RmsnormParams = STRUCTS["dimsum_rmsnorm_params"]
 GeluMulParams = STRUCTS["dimsum_gelu_mul_params"]
 NormModulateParams = STRUCTS["dimsum_norm_modulate_params"]
+ColsumParams = STRUCTS["dimsum_colsum_params"]
+GeluMulBwdParams = STRUCTS["dimsum_gelu_mul_bwd_params"]
 
 ENTRY_POINTS = {
     "dimsum_selective_scan_fwd": ScanFwdParams,
@@ -128,6 +130,8 @@ ENTRY_POINTS = {
     "dimsum_add_rmsnorm": RmsnormParams,
     "dimsum_gelu_mul": GeluMulParams,
     "dimsum_norm_modulate": NormModulateParams,
+    "dimsum_token_colsum": ColsumParams,
+    "dimsum_gelu_mul_bwd": GeluMulBwdParams,
 }
 
 

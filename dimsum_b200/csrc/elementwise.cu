@@ -227,6 +227,77 @@ __global__ void __launch_bounds__(256) gelu_mul_kernel(const dimsum_gelu_mul_par
     }
 }
 
+// column sums over the tokens of a batch row: CTA = (128 channels, batch row); 8 warps stride over the tokens, a lane
+// owns 4 consecutive channels, partial sums meet in shared memory
+__global__ void __launch_bounds__(256) colsum_kernel(const dimsum_colsum_params p) {
+    __shared__ float red[2][8][128];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c0 = blockIdx.x * 128 + lane * 4;
+    const int64_t b = blockIdx.y;
+    const bool want_x = p.sum_gx != nullptr;
+    float sg[4] = {0.f, 0.f, 0.f, 0.f}, sx[4] = {0.f, 0.f, 0.f, 0.f};
+    if (c0 < p.channels) {
+        for (int l = warp; l < p.seqlen; l += 8) {
+            float g[4], x[4];
+            ld_rt<4>(p.g, (int)p.g_dtype, b * p.g_batch_stride + (int64_t)l * p.g_token_stride + c0, g);
+            if (want_x) ld_rt<4>(p.x, (int)p.x_dtype, b * p.x_batch_stride + (int64_t)l * p.x_token_stride + c0, x);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                sg[i] += g[i];
+                if (want_x) sx[i] = fmaf(g[i], x[i], sx[i]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { red[0][warp][lane * 4 + i] = sg[i]; red[1][warp][lane * 4 + i] = sx[i]; }
+    __syncthreads();
+    const int which = threadIdx.x >> 7, c = threadIdx.x & 127;           // 256 threads: 2 outputs x 128 channels
+    void *dst = which ? p.sum_gx : p.sum_g;
+    if (dst != nullptr && blockIdx.x * 128 + c < p.channels) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += red[which][w][c];
+        const int64_t o = b * p.out_row_stride + blockIdx.x * 128 + c;
+        if (p.out_dtype == DIMSUM_F32) reinterpret_cast<float *>(dst)[o] = t;
+        else if (p.out_dtype == DIMSUM_BF16) reinterpret_cast<__nv_bfloat16 *>(dst)[o] = __float2bfloat16_rn(t);
+        else reinterpret_cast<__half *>(dst)[o] = __float2half_rn(t);
+    }
+}
+
+// d/dx of the tanh-approximated GELU, sharing the tanh with the value
+DEV void gelu_tanh_with_grad(float x, float &val, float &grad) {
+    const float k = 0.7978845608028654f, c = 0.044715f;
+    const float x2 = x * x;
+    const float y = k * fmaf(c * x2, x, x);
+    const float t = 1.f - 2.f * rcp_mufu(1.f + ex2_mufu(2.f * kLog2e * y));
+    val = 0.5f * x * (1.f + t);
+    grad = 0.5f * (1.f + t) + 0.5f * x * (1.f - t * t) * k * fmaf(3.f * c, x2, 1.f);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) gelu_mul_bwd_kernel(const dimsum_gelu_mul_bwd_params p) {
+    constexpr int VEC = Io<T>::kVec;
+    const unsigned tpr = (unsigned)(p.hidden / VEC);
+    const int64_t r = blockIdx.y + (int64_t)blockIdx.z * gridDim.y;
+    const unsigned v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= tpr || r >= p.rows) return;
+    const T *x = reinterpret_cast<const T *>(p.x) + r * p.x_row_stride + v * VEC;
+    float a[VEC], b[VEC], g[VEC], da[VEC], db[VEC];
+    Io<T>::ldv(x, a);
+    Io<T>::ldv(x + p.hidden, b);
+    Io<T>::ldv(reinterpret_cast<const T *>(p.dy) + r * p.dy_row_stride + v * VEC, g);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        float val, grad;
+        gelu_tanh_with_grad(a[i], val, grad);
+        da[i] = g[i] * b[i] * grad;
+        db[i] = g[i] * val;
+    }
+    T *dx = reinterpret_cast<T *>(p.dx) + r * p.dx_row_stride + v * VEC;
+    Io<T>::stv(dx, da);
+    Io<T>::stv(dx + p.hidden, db);
+}
+
 int rowwise_entry(const dimsum_rowwise_params *p, bool gate, void *stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     const char *who = gate ? "gate_residual" : "modulate";
@@ -303,4 +374,40 @@ extern "C" int dimsum_gelu_mul(const dimsum_gelu_mul_params *p, void *stream_) {
     else { GM(__half) }
 #undef GM
     return check_launch("gelu_mul");
+}
+
+extern "C" int dimsum_token_colsum(const dimsum_colsum_params *p, void *stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (p != nullptr && p->batch == 0) return DIMSUM_OK;
+    DIMSUM_REQUIRE(p != nullptr && p->g && (p->sum_g || p->sum_gx), DIMSUM_ERR_INVALID, "token_colsum: null pointer");
+    DIMSUM_REQUIRE(p->sum_gx == nullptr || p->x != nullptr, DIMSUM_ERR_INVALID, "token_colsum: sum_gx needs x");
+    DIMSUM_REQUIRE(p->batch > 0 && p->seqlen > 0 && p->channels > 0, DIMSUM_ERR_INVALID, "token_colsum: bad sizes");
+    auto dt_ok = [](int64_t d) { return d >= 0 && d <= 2; };
+    DIMSUM_REQUIRE(dt_ok(p->g_dtype) && dt_ok(p->out_dtype) && (p->x == nullptr || dt_ok(p->x_dtype)), DIMSUM_ERR_INVALID,
+                   "token_colsum: unknown dtype");
+    DIMSUM_REQUIRE(p->channels % 4 == 0 && aligned16(p->g) && p->g_batch_stride % 4 == 0 && p->g_token_stride % 4 == 0 &&
+                       (p->x == nullptr || (aligned16(p->x) && p->x_batch_stride % 4 == 0 && p->x_token_stride % 4 == 0)),
+                   DIMSUM_ERR_UNSUPPORTED, "token_colsum: rows must be 16-byte aligned and channels a multiple of 4");
+    DIMSUM_REQUIRE(p->batch <= 65535, DIMSUM_ERR_UNSUPPORTED, "token_colsum: batch > 65535");
+    colsum_kernel<<<dim3((unsigned)((p->channels + 127) / 128), (unsigned)p->batch), 256, 0, stream>>>(*p);
+    return check_launch("token_colsum");
+}
+
+extern "C" int dimsum_gelu_mul_bwd(const dimsum_gelu_mul_bwd_params *p, void *stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (p != nullptr && p->rows == 0) return DIMSUM_OK;
+    DIMSUM_REQUIRE(p != nullptr && p->x && p->dy && p->dx, DIMSUM_ERR_INVALID, "gelu_mul_bwd: null pointer");
+    DIMSUM_REQUIRE(p->rows > 0 && p->hidden > 0 && p->dtype >= 0 && p->dtype <= 2, DIMSUM_ERR_INVALID, "gelu_mul_bwd: bad arguments");
+    const int vec = p->dtype == DIMSUM_F32 ? 4 : 8;
+    DIMSUM_REQUIRE(p->hidden % vec == 0 && aligned16(p->x) && aligned16(p->dy) && aligned16(p->dx) && p->x_row_stride % vec == 0 &&
+                       p->dy_row_stride % vec == 0 && p->dx_row_stride % vec == 0,
+                   DIMSUM_ERR_UNSUPPORTED, "gelu_mul_bwd: rows must be 16-byte aligned");
+    const unsigned tpr = (unsigned)(p->hidden / vec);
+    const unsigned gy = (unsigned)(p->rows < 65535 ? p->rows : 65535), gz = (unsigned)((p->rows + gy - 1) / gy);
+    DIMSUM_REQUIRE(gz <= 65535, DIMSUM_ERR_UNSUPPORTED, "gelu_mul_bwd: too many rows");
+    const dim3 grid((tpr + 255) / 256, gy, gz);
+    if (p->dtype == DIMSUM_F32) gelu_mul_bwd_kernel<float><<<grid, 256, 0, stream>>>(*p);
+    else if (p->dtype == DIMSUM_BF16) gelu_mul_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(*p);
+    else gelu_mul_bwd_kernel<__half><<<grid, 256, 0, stream>>>(*p);
+    return check_launch("gelu_mul_bwd");
 }

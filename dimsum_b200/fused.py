@@ -2,7 +2,8 @@
 row index) and residual-add + RMSNorm.  Reference: `modulate` dimsum/models_dim.py:34-35, the gated residuals
 :1510-1512 / :686-689, the transpose / flip copies :1498-1524, and the Triton `rms_norm_fn`
 (mamba/mamba_ssm/ops/triton/layernorm.py:460).  One coalesced pass each; no permuted copy is materialised.
-These have no autograd: the model uses them when gradients are off (sampling) and plain torch ops when training.
+The raw kernels have no autograd; `modulate_fn`, `gate_residual_fn` and `gelu_mul_fn` at the end of the file wrap them in
+autograd Functions (backward = the same streaming kernels plus `dimsum_token_colsum` / `dimsum_gelu_mul_bwd`) for training.
 """
 import torch
 
@@ -146,3 +147,122 @@ def gelu_mul(x12):
         p.x, p.y = x2.data_ptr(), y.data_ptr()
         _lib.call("dimsum_gelu_mul", p, torch.cuda.current_stream(x12.device).cuda_stream)
     return y.view(shape[:-1] + (H,))
+
+
+# ---------------------------------------------------------------------------------------------------
+# training: the same kernels under autograd
+# ---------------------------------------------------------------------------------------------------
+def token_colsum(g, x=None, want_sum_g=True, out_dtype=None):
+    """-> (sum_l g[b, l, :], sum_l g[b, l, :] * x[b, l, :]) as (batch, channels) tensors (None where not requested)."""
+    _rows(g, "g")
+    if x is not None:
+        _rows(x, "x")
+        if x.shape != g.shape:
+            raise RuntimeError("token_colsum: x must have the shape of g")
+    B, L, C = g.shape
+    out_dtype = out_dtype or g.dtype
+    sum_g = torch.empty((B, C), device=g.device, dtype=out_dtype) if want_sum_g else None
+    sum_gx = torch.empty((B, C), device=g.device, dtype=out_dtype) if x is not None else None
+    with torch.cuda.device(g.device):
+        p = _lib.ColsumParams()
+        p.batch, p.seqlen, p.channels = B, L, C
+        p.g_dtype, p.x_dtype, p.out_dtype = _DT[g.dtype], _DT[x.dtype] if x is not None else 0, _DT[out_dtype]
+        p.g_batch_stride, p.g_token_stride = g.stride(0), g.stride(1)
+        if x is not None:
+            p.x_batch_stride, p.x_token_stride = x.stride(0), x.stride(1)
+        p.out_row_stride = C
+        p.g, p.x = g.data_ptr(), x.data_ptr() if x is not None else None
+        p.sum_g = sum_g.data_ptr() if sum_g is not None else None
+        p.sum_gx = sum_gx.data_ptr() if sum_gx is not None else None
+        _lib.call("dimsum_token_colsum", p, torch.cuda.current_stream(g.device).cuda_stream)
+    return sum_g, sum_gx
+
+
+def _rows_ok(t):
+    return t if t.stride(2) == 1 else t.contiguous()
+
+
+class _ModulateFn(torch.autograd.Function):
+    """y = x * (1 + scale[:, None]) + shift[:, None] (models_dim.py:34-35) in the promoted dtype of x and scale."""
+
+    @staticmethod
+    def forward(ctx, x, shift, scale):
+        x = _rows_ok(x)
+        ctx.save_for_backward(x, scale)
+        ctx.shift_dtype = shift.dtype
+        return modulate(x, shift, scale, out_dtype=torch.promote_types(x.dtype, scale.dtype))
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, scale = ctx.saved_tensors
+        gy = _rows_ok(gy)
+        zero = torch.zeros(scale.shape, device=scale.device, dtype=scale.dtype)
+        if zero.stride(0) != scale.stride(0):
+            scale = scale.contiguous()
+        gx = modulate(gy, zero, scale, out_dtype=x.dtype) if ctx.needs_input_grad[0] else None
+        gshift, gscale = token_colsum(gy, x, want_sum_g=True, out_dtype=ctx.shift_dtype)
+        return gx, gshift, gscale
+
+
+class _GateResidualFn(torch.autograd.Function):
+    """out = x + gate[:, None] * m (models_dim.py:1510-1512) in the promoted dtype of x and gate."""
+
+    @staticmethod
+    def forward(ctx, x, gate, m):
+        x, m = _rows_ok(x), _rows_ok(m)
+        ctx.save_for_backward(gate, m)
+        ctx.x_dtype = x.dtype
+        return gate_residual(x, gate, m, out_dtype=torch.promote_types(x.dtype, gate.dtype))
+
+    @staticmethod
+    def backward(ctx, gy):
+        gate, m = ctx.saved_tensors
+        gy = _rows_ok(gy)
+        gx = gy if gy.dtype == ctx.x_dtype else gy.to(ctx.x_dtype)
+        gm = None
+        if ctx.needs_input_grad[2]:
+            gm1 = (gate - 1).contiguous()                          # gy * gate = gy * (1 + (gate - 1)) + 0
+            gm = modulate(gy, torch.zeros_like(gm1), gm1, out_dtype=m.dtype)
+        _, ggate = token_colsum(gy, m, want_sum_g=False, out_dtype=gate.dtype)
+        return gx, ggate, gm
+
+
+class _GeluMulFn(torch.autograd.Function):
+    """gelu_tanh(x12[..., :H]) * x12[..., H:] (mlp.py:65-70)."""
+
+    @staticmethod
+    def forward(ctx, x12):
+        ctx.save_for_backward(x12)
+        return gelu_mul(x12)
+
+    @staticmethod
+    def backward(ctx, gy):
+        (x12,) = ctx.saved_tensors
+        shape = x12.shape
+        x2 = x12.reshape(-1, shape[-1])
+        g2 = gy.reshape(-1, gy.shape[-1])
+        if x2.stride(1) != 1:
+            x2 = x2.contiguous()
+        if g2.stride(1) != 1 or g2.dtype != x2.dtype:
+            g2 = g2.to(x2.dtype).contiguous()
+        rows, twoH = x2.shape
+        dx = torch.empty((rows, twoH), device=x12.device, dtype=x12.dtype)
+        with torch.cuda.device(x12.device):
+            p = _lib.GeluMulBwdParams()
+            p.rows, p.hidden, p.dtype = rows, twoH // 2, _DT[x12.dtype]
+            p.x_row_stride, p.dy_row_stride, p.dx_row_stride = x2.stride(0), g2.stride(0), dx.stride(0)
+            p.x, p.dy, p.dx = x2.data_ptr(), g2.data_ptr(), dx.data_ptr()
+            _lib.call("dimsum_gelu_mul_bwd", p, torch.cuda.current_stream(x12.device).cuda_stream)
+        return dx.view(shape)
+
+
+def modulate_fn(x, shift, scale):
+    return _ModulateFn.apply(x, shift, scale)
+
+
+def gate_residual_fn(x, gate, m):
+    return _GateResidualFn.apply(x, gate, m if m.dtype == gate.dtype else m.to(gate.dtype))
+
+
+def gelu_mul_fn(x12):
+    return _GeluMulFn.apply(x12)

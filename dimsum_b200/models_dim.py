@@ -16,6 +16,7 @@ Hot-path differences from the reference (same results, fewer HBM passes):
 Dense layers (in/x/dt/out projections, attention, MLP) are cuBLAS / SDPA calls, as in the reference.
 """
 import math
+import os
 from functools import partial
 
 import numpy as np
@@ -38,12 +39,24 @@ def _fused_ok(x):
     return x.is_cuda and not torch.is_grad_enabled()
 
 
+_GLUE_DTYPES = (torch.float32, torch.bfloat16, torch.float16)
+
+
+def _train_fused_ok(x, *others):
+    """Recorded (training) pass on CUDA: the same glue kernels under autograd (fused.modulate_fn & co) unless
+    DIMSUM_TRAIN_FUSED=0 asks for the plain PyTorch expressions."""
+    return (x.is_cuda and x.dim() == 3 and x.shape[-1] % 8 == 0 and os.environ.get("DIMSUM_TRAIN_FUSED", "1") != "0"
+            and all(t.dtype in _GLUE_DTYPES for t in (x,) + others))
+
+
 def _mod(x, shift, scale, idx=None):
     if _fused_ok(x):
         # under autocast the consumer is a low-precision GEMM: emit its input dtype directly (no separate cast pass)
         out_dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else None
         return fused.modulate(x, shift, scale, idx, out_dtype=out_dtype)
     assert idx is None
+    if _train_fused_ok(x, shift, scale):
+        return fused.modulate_fn(x, shift, scale)
     return modulate(x, shift, scale)
 
 
@@ -69,6 +82,8 @@ def _gated(x, gate, m, idx=None, feeds_gemm=False):
         out_dtype = torch.get_autocast_dtype("cuda") if feeds_gemm and torch.is_autocast_enabled() else None
         return fused.gate_residual(x, gate, m, idx, out_dtype=out_dtype)
     assert idx is None
+    if _train_fused_ok(x, gate, m) and m.shape == x.shape:
+        return fused.gate_residual_fn(x, gate, m)
     return x + gate.unsqueeze(1) * m
 
 
@@ -169,6 +184,8 @@ class GatedMLP(nn.Module):
         x12 = self.w12(x)
         if _fused_ok(x12) and x12.dtype in (torch.float32, torch.bfloat16, torch.float16):
             return self.w3(fused.gelu_mul(x12))
+        if _train_fused_ok(x12) and isinstance(self.act_layer, nn.GELU) and self.act_layer.approximate == "tanh":
+            return self.w3(fused.gelu_mul_fn(x12))
         x1, x2 = x12.chunk(2, dim=-1)
         return self.w3(self.act_layer(x1) * x2)
 

@@ -250,6 +250,33 @@ typedef struct {
 
 int dimsum_gelu_mul(const dimsum_gelu_mul_params *p, void *stream);
 
+/* ---- backward pieces of the glue (training) ------------------------------------------------ */
+/* Column sums over the tokens of each batch row, the reductions autograd needs for adaLN modulate / gated residual
+ * (d shift = sum_l g, d scale = sum_l g x, d gate = sum_l g m; reference: autograd through models_dim.py:34-35, 1509-1512):
+ *     sum_g[b, c] = sum_l g[b, l, c]            sum_gx[b, c] = sum_l g[b, l, c] * x[b, l, c]
+ * g, x: (batch, seqlen, channels) with channel stride 1, any of the three dtypes; either output may be NULL (x may be NULL
+ * when sum_gx is); outputs (batch, channels) in out_dtype with row stride out_row_stride.  channels % 4 == 0.
+ */
+typedef struct {
+    int64_t batch, seqlen, channels;
+    int64_t g_dtype, x_dtype, out_dtype;
+    int64_t g_batch_stride, g_token_stride, x_batch_stride, x_token_stride, out_row_stride;
+    const void *g, *x;
+    void *sum_g, *sum_gx;
+} dimsum_colsum_params;
+
+int dimsum_token_colsum(const dimsum_colsum_params *p, void *stream);
+
+/* backward of dimsum_gelu_mul: dx[r, :H] = dy * x[r, H:] * gelu_tanh'(x[r, :H]), dx[r, H:] = dy * gelu_tanh(x[r, :H]). */
+typedef struct {
+    int64_t rows, hidden, dtype;
+    int64_t x_row_stride, dy_row_stride, dx_row_stride;
+    const void *x, *dy;
+    void *dx;
+} dimsum_gelu_mul_bwd_params;
+
+int dimsum_gelu_mul_bwd(const dimsum_gelu_mul_bwd_params *p, void *stream);
+
 /* ---- misc --------------------------------------------------------------------------------- */
 int dimsum_abi_version(void);
 const char *dimsum_last_error(void);

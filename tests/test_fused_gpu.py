@@ -107,3 +107,46 @@ def test_norm_modulate_rejects_bad_arguments():
     with pytest.raises(NotImplementedError):
         big = torch.randn(1, 2, 4096, device="cuda")
         fused.norm_modulate(big, None, torch.ones(4096, device="cuda"), 1e-5, big[:, 0], big[:, 0])   # > 1024 fp32 channels
+
+
+@pytest.mark.parametrize("x_dtype,aux_dtype", [(torch.float32, torch.float32), (torch.float32, torch.bfloat16),
+                                               (torch.bfloat16, torch.bfloat16)])
+def test_training_glue_functions_match_autograd(x_dtype, aux_dtype):
+    """modulate_fn / gate_residual_fn / gelu_mul_fn: values and every gradient against the PyTorch expressions they replace in
+    the recorded pass (models_dim.py:34-35, 1510-1512; mlp.py:65-70), including the mixed dtypes autocast produces."""
+    import torch.nn.functional as F
+    from dimsum_b200 import fused
+    g = torch.Generator(device="cuda").manual_seed(4)
+    B, L, C = 3, 50, 256
+    low = x_dtype != torch.float32 or aux_dtype != torch.float32
+    tol_v, tol_g = (1e-2, 2e-2) if low else (1e-6, 2e-5)
+
+    def leaf(*shape, dtype):
+        return torch.randn(*shape, generator=g, device="cuda").to(dtype).requires_grad_(True)
+
+    x, m = leaf(B, L, C, dtype=x_dtype), leaf(B, L, C, dtype=aux_dtype)
+    ada = leaf(B, 3 * C, dtype=aux_dtype)
+    for fn_fused, fn_ref in ((lambda sh, sc, gt: fused.modulate_fn(x, sh, sc), lambda sh, sc, gt: x * (1 + sc.unsqueeze(1)) + sh.unsqueeze(1)),
+                             (lambda sh, sc, gt: fused.gate_residual_fn(x, gt, m), lambda sh, sc, gt: x + gt.unsqueeze(1) * m)):
+        outs = []
+        for fn in (fn_fused, fn_ref):
+            for t in (x, m, ada):
+                t.grad = None
+            y = fn(*ada.chunk(3, dim=1))
+            gy = torch.randn(y.shape, generator=torch.Generator(device="cuda").manual_seed(9), device="cuda").to(y.dtype)
+            y.backward(gy)
+            outs.append((y.detach(), x.grad.clone(), ada.grad.clone(), None if m.grad is None else m.grad.clone()))
+        (y1, gx1, ga1, gm1), (y2, gx2, ga2, gm2) = outs
+        assert y1.dtype == y2.dtype and rel_err(y1, y2) <= tol_v
+        assert gx1.dtype == gx2.dtype and rel_err(gx1, gx2) <= tol_g
+        assert ga1.dtype == ga2.dtype and rel_err(ga1, ga2) <= tol_g
+        if gm2 is not None:
+            assert gm1.dtype == gm2.dtype and rel_err(gm1, gm2) <= tol_g
+    x12 = leaf(B * L, 2 * C, dtype=x_dtype)
+    outs = []
+    for fn in (fused.gelu_mul_fn, lambda t: F.gelu(t[:, :C], approximate="tanh") * t[:, C:]):
+        x12.grad = None
+        y = fn(x12)
+        y.backward(torch.ones_like(y) * 0.5)
+        outs.append((y.detach(), x12.grad.clone()))
+    assert rel_err(outs[0][0], outs[1][0]) <= tol_v and rel_err(outs[0][1], outs[1][1]) <= tol_g
