@@ -116,6 +116,7 @@ GeluMulParams = STRUCTS["dimsum_gelu_mul_params"]
 NormModulateParams = STRUCTS["dimsum_norm_modulate_params"]
 ColsumParams = STRUCTS["dimsum_colsum_params"]
 GeluMulBwdParams = STRUCTS["dimsum_gelu_mul_bwd_params"]
+RmsnormBwdParams = STRUCTS["dimsum_rmsnorm_bwd_params"]
 
 ENTRY_POINTS = {
     "dimsum_selective_scan_fwd": ScanFwdParams,
@@ -132,6 +133,7 @@ ENTRY_POINTS = {
     "dimsum_norm_modulate": NormModulateParams,
     "dimsum_token_colsum": ColsumParams,
     "dimsum_gelu_mul_bwd": GeluMulBwdParams,
+    "dimsum_add_rmsnorm_bwd": RmsnormBwdParams,
 }
 
 

@@ -298,6 +298,88 @@ __global__ void __launch_bounds__(256) gelu_mul_bwd_kernel(const dimsum_gelu_mul
     Io<T>::stv(dx + p.hidden, db);
 }
 
+// RMSNorm backward: one warp per row (the fp32 row h lives in registers), a CTA's 8 warps walk rows blockIdx.x*8+warp,
+// += gridDim.x*8, ... and keep their dweight contributions in registers; one shared-memory reduction per CTA at the end
+template <int kMaxIter>
+__global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const dimsum_rmsnorm_bwd_params p) {
+    __shared__ float red[8][32 * kMaxIter * 4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nvec = (int)(p.channels / 4);
+    const float *w = reinterpret_cast<const float *>(p.weight);
+    float wv[kMaxIter][4], dw[kMaxIter][4];
+#pragma unroll
+    for (int it = 0; it < kMaxIter; ++it) {
+        const int v = lane + it * 32;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { dw[it][i] = 0.f; wv[it][i] = v < nvec ? w[v * 4 + i] : 0.f; }
+    }
+    const float inv_c = 1.f / (float)p.channels;
+    for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < p.rows; row += (int64_t)gridDim.x * 8) {
+        const float *h = reinterpret_cast<const float *>(p.h) + row * p.channels;
+        float hv[kMaxIter][4], gv[kMaxIter][4];
+        float ss = 0.f;
+#pragma unroll
+        for (int it = 0; it < kMaxIter; ++it) {
+            const int v = lane + it * 32;
+            if (v < nvec) {
+                Io<float>::ld4(h + v * 4, hv[it]);
+                ld_rt<4>(p.dy, (int)p.dy_dtype, row * p.dy_row_stride + v * 4, gv[it]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) ss = fmaf(hv[it][i], hv[it][i], ss);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { hv[it][i] = 0.f; gv[it][i] = 0.f; }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        const float rstd = rsqrtf(ss * inv_c + p.eps);
+        float c1 = 0.f;
+#pragma unroll
+        for (int it = 0; it < kMaxIter; ++it) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                hv[it][i] *= rstd;                                   // xhat
+                dw[it][i] = fmaf(gv[it][i], hv[it][i], dw[it][i]);
+                gv[it][i] *= wv[it][i];                              // weight * dy
+                c1 = fmaf(gv[it][i], hv[it][i], c1);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+        c1 *= inv_c;
+#pragma unroll
+        for (int it = 0; it < kMaxIter; ++it) {
+            const int v = lane + it * 32;
+            if (v < nvec) {
+                float d[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) d[i] = (gv[it][i] - hv[it][i] * c1) * rstd;
+                if (p.dres_in != nullptr) {
+                    float r[4];
+                    Io<float>::ld4(reinterpret_cast<const float *>(p.dres_in) + row * p.channels + v * 4, r);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) d[i] += r[i];
+                }
+                st_rt<4>(p.dx, (int)p.dx_dtype, row * p.dx_row_stride + v * 4, d);
+                if (p.dres_out != nullptr) Io<float>::st4(reinterpret_cast<float *>(p.dres_out) + row * p.channels + v * 4, d);
+            }
+        }
+    }
+#pragma unroll
+    for (int it = 0; it < kMaxIter; ++it)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) red[warp][(lane + it * 32) * 4 + i] = dw[it][i];
+    __syncthreads();
+    float *dst = reinterpret_cast<float *>(p.dweight_partial) + (int64_t)blockIdx.x * p.channels;
+    for (int c = threadIdx.x; c < p.channels; c += 256) {
+        float t = 0.f;
+#pragma unroll
+        for (int wp = 0; wp < 8; ++wp) t += red[wp][c];
+        dst[c] = t;
+    }
+}
+
 int rowwise_entry(const dimsum_rowwise_params *p, bool gate, void *stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     const char *who = gate ? "gate_residual" : "modulate";
@@ -410,4 +492,24 @@ extern "C" int dimsum_gelu_mul_bwd(const dimsum_gelu_mul_bwd_params *p, void *st
     else if (p->dtype == DIMSUM_BF16) gelu_mul_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(*p);
     else gelu_mul_bwd_kernel<__half><<<grid, 256, 0, stream>>>(*p);
     return check_launch("gelu_mul_bwd");
+}
+
+extern "C" int dimsum_add_rmsnorm_bwd(const dimsum_rmsnorm_bwd_params *p, void *stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    DIMSUM_REQUIRE(p != nullptr && p->h && p->weight && p->dy && p->dx && p->dweight_partial, DIMSUM_ERR_INVALID,
+                   "add_rmsnorm_bwd: null pointer");
+    DIMSUM_REQUIRE(p->rows > 0 && p->channels > 0 && p->n_partials > 0, DIMSUM_ERR_INVALID, "add_rmsnorm_bwd: bad sizes");
+    DIMSUM_REQUIRE(p->dy_dtype >= 0 && p->dy_dtype <= 2 && p->dx_dtype >= 0 && p->dx_dtype <= 2, DIMSUM_ERR_INVALID,
+                   "add_rmsnorm_bwd: unknown dtype");
+    DIMSUM_REQUIRE(p->channels % 4 == 0 && p->channels <= 1024, DIMSUM_ERR_UNSUPPORTED,
+                   "add_rmsnorm_bwd: channels=%lld must be a multiple of 4 and at most 1024", (long long)p->channels);
+    DIMSUM_REQUIRE(aligned16(p->h) && aligned16(p->dy) && aligned16(p->dx) && p->dy_row_stride % 4 == 0 && p->dx_row_stride % 4 == 0 &&
+                       (p->dres_in == nullptr || aligned16(p->dres_in)) && (p->dres_out == nullptr || aligned16(p->dres_out)),
+                   DIMSUM_ERR_UNSUPPORTED, "add_rmsnorm_bwd: rows must be 16-byte aligned");
+    const unsigned blocks = (unsigned)p->n_partials;
+    const int per_lane = (int)((p->channels / 4 + 31) / 32);
+    if (per_lane <= 2) rmsnorm_bwd_kernel<2><<<blocks, 256, 0, stream>>>(*p);
+    else if (per_lane <= 4) rmsnorm_bwd_kernel<4><<<blocks, 256, 0, stream>>>(*p);
+    else rmsnorm_bwd_kernel<8><<<blocks, 256, 0, stream>>>(*p);
+    return check_launch("add_rmsnorm_bwd");
 }

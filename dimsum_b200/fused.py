@@ -256,6 +256,53 @@ class _GeluMulFn(torch.autograd.Function):
         return dx.view(shape)
 
 
+class _AddRmsNormFn(torch.autograd.Function):
+    """(y, h) = (rmsnorm(x + residual) * weight, x + residual in fp32); backward by `dimsum_add_rmsnorm_bwd`."""
+
+    @staticmethod
+    def forward(ctx, x, residual, weight, eps):
+        y, h = add_rmsnorm(x, residual, weight, eps, want_residual=True)
+        ctx.save_for_backward(h, weight)
+        ctx.eps, ctx.x_dtype, ctx.has_res = eps, x.dtype, residual is not None
+        return y, h
+
+    @staticmethod
+    def backward(ctx, gy, gh):
+        h, weight = ctx.saved_tensors
+        shape = h.shape
+        C = shape[-1]
+        h2 = h.reshape(-1, C)
+        g2 = gy.reshape(-1, C)
+        if g2.stride(1) != 1:
+            g2 = g2.contiguous()
+        if gh is not None:
+            gh = gh.reshape(-1, C)
+            gh = gh.float().contiguous() if (gh.dtype != torch.float32 or not gh.is_contiguous()) else gh
+        rows = h2.shape[0]
+        n_part = max(1, min((rows + 7) // 8, 2 * torch.cuda.get_device_properties(h.device).multi_processor_count))
+        dx = torch.empty((rows, C), device=h.device, dtype=ctx.x_dtype)
+        dres = torch.empty((rows, C), device=h.device, dtype=torch.float32) if ctx.has_res else None
+        part = torch.empty((n_part, C), device=h.device, dtype=torch.float32)
+        w = weight.float().contiguous()
+        with torch.cuda.device(h.device):
+            p = _lib.RmsnormBwdParams()
+            p.rows, p.channels, p.n_partials = rows, C, n_part
+            p.dy_dtype, p.dx_dtype = _DT[g2.dtype], _DT[dx.dtype]
+            p.dy_row_stride, p.dx_row_stride = g2.stride(0), dx.stride(0)
+            p.h, p.weight, p.dy = h2.data_ptr(), w.data_ptr(), g2.data_ptr()
+            p.dres_in = gh.data_ptr() if gh is not None else None
+            p.dx, p.dweight_partial = dx.data_ptr(), part.data_ptr()
+            p.dres_out = dres.data_ptr() if dres is not None else None
+            p.eps = ctx.eps
+            _lib.call("dimsum_add_rmsnorm_bwd", p, torch.cuda.current_stream(h.device).cuda_stream)
+        return dx.view(shape), (dres.view(shape) if dres is not None else None), part.sum(0).to(weight.dtype), None
+
+
+def add_rmsnorm_fn(x, residual, weight, eps):
+    """-> (y, h) with autograd: y = rmsnorm(x + residual) * weight in x.dtype, h = x + residual in fp32."""
+    return _AddRmsNormFn.apply(x, residual, weight, eps)
+
+
 def modulate_fn(x, shift, scale):
     return _ModulateFn.apply(x, shift, scale)
 

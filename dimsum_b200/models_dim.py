@@ -101,6 +101,10 @@ class RMSNorm(nn.Module):
         if _fused_ok(x) and (residual is None or residual.dtype == torch.float32) and (residual_in_fp32 or not prenorm):
             y, res = fused.add_rmsnorm(x, residual, self.weight, self.eps, want_residual=prenorm)
             return (y, res) if prenorm else y
+        if (_train_fused_ok(x) and x.shape[-1] <= 1024 and x.shape[-1] % 8 == 0 and self.weight.dtype == torch.float32
+                and (residual is None or residual.dtype == torch.float32) and (residual_in_fp32 or not prenorm)):
+            y, res = fused.add_rmsnorm_fn(x, residual, self.weight, self.eps)
+            return (y, res) if prenorm else y
         io_dtype = x.dtype
         xf = x.float()
         if residual is not None:

@@ -277,6 +277,25 @@ typedef struct {
 
 int dimsum_gelu_mul_bwd(const dimsum_gelu_mul_bwd_params *p, void *stream);
 
+/* backward of dimsum_add_rmsnorm (autograd through rms_norm_ref, layernorm.py:32-47):
+ *     xhat = h * rstd,  rstd = rsqrt(mean(h^2) + eps),  h = x + residual (fp32, the forward's res_out)
+ *     dh = (weight * dy - xhat * mean(weight * dy * xhat)) * rstd + dres_in          (dres_in may be NULL)
+ *     dweight_partial[cta, c] = sum over the rows of that CTA of dy[r, c] * xhat[r, c]
+ * dh is written as dx (dx_dtype) and, when dres_out != NULL, as fp32 dres_out.  h, dres_in, dres_out: (rows, channels) fp32
+ * contiguous; dy: y_dtype with row stride dy_row_stride; dweight_partial: (n_partials, channels) fp32, one row per CTA, the
+ * caller sums them (deterministic, no atomics).  channels % 4 == 0, channels <= 1024.
+ */
+typedef struct {
+    int64_t rows, channels, n_partials;
+    int64_t dy_dtype, dx_dtype;
+    int64_t dy_row_stride, dx_row_stride;
+    const void *h, *weight, *dy, *dres_in;
+    void *dx, *dres_out, *dweight_partial;
+    float eps;
+} dimsum_rmsnorm_bwd_params;
+
+int dimsum_add_rmsnorm_bwd(const dimsum_rmsnorm_bwd_params *p, void *stream);
+
 /* ---- misc --------------------------------------------------------------------------------- */
 int dimsum_abi_version(void);
 const char *dimsum_last_error(void);

@@ -150,3 +150,38 @@ def test_training_glue_functions_match_autograd(x_dtype, aux_dtype):
         y.backward(torch.ones_like(y) * 0.5)
         outs.append((y.detach(), x12.grad.clone()))
     assert rel_err(outs[0][0], outs[1][0]) <= tol_v and rel_err(outs[0][1], outs[1][1]) <= tol_g
+
+
+@pytest.mark.parametrize("x_dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("C,with_res", [(1024, True), (512, False), (64, True)])
+def test_add_rmsnorm_fn_gradients_match_autograd(x_dtype, C, with_res):
+    """add_rmsnorm_fn (prenorm residual stream in fp32) against autograd through the rms_norm_ref maths (layernorm.py:32-47)."""
+    from dimsum_b200 import fused
+    g = torch.Generator(device="cuda").manual_seed(5)
+    B, L = 3, 41
+    x = torch.randn(B, L, C, generator=g, device="cuda").to(x_dtype).requires_grad_(True)
+    res = torch.randn(B, L, C, generator=g, device="cuda").requires_grad_(True) if with_res else None
+    w = (1 + 0.1 * torch.randn(C, generator=g, device="cuda")).requires_grad_(True)
+    gy = torch.randn(B, L, C, generator=g, device="cuda").to(x_dtype)
+    gh = torch.randn(B, L, C, generator=g, device="cuda")
+
+    def ref():
+        h = x.float() + (res if res is not None else 0)
+        y = (h * torch.rsqrt(h.square().mean(-1, keepdim=True) + 1e-5) * w).to(x_dtype)
+        return y, h
+
+    outs = []
+    for fn in (lambda: fused.add_rmsnorm_fn(x, res, w, 1e-5), ref):
+        for t in (x, res, w):
+            if t is not None:
+                t.grad = None
+        y, h = fn()
+        torch.autograd.backward([y, h], [gy, gh])
+        outs.append((y.detach(), h.detach(), x.grad.clone(), None if res is None else res.grad.clone(), w.grad.clone()))
+    low = x_dtype != torch.float32
+    for name, a, b in zip(("y", "h", "dx", "dres", "dw"), *outs):
+        if b is None:
+            assert a is None
+            continue
+        assert a.dtype == b.dtype and a.shape == b.shape, name
+        assert rel_err(a, b) <= (2e-2 if low and name in ("y", "dx") else 1e-2 if low else 3e-5), (name, rel_err(a, b))
