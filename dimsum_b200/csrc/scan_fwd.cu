@@ -18,6 +18,7 @@
 //     S4D-real initialisation A = -(1..N) of mamba_simple.py:514-521 and checked on the host -- the 16 decays of a step
 //     are the powers r, r^2, .. r^16 of ONE exp (kArith): 1 MUFU + 8 packed multiplies instead of 16 MUFU.  Moving
 //     part of the exps to a polynomial on the FMA pipe was measured and is slower (profiles/r1_scan_fwd_experiments.md).
+#include <atomic>
 #include <type_traits>
 
 #include "common.cuh"
@@ -333,12 +334,13 @@ int launch(const ScanFwdArgs &a, int batch, cudaStream_t stream) {
     constexpr int LC = kRowBytes / (int)sizeof(T);
     auto kern = scan_fwd_kernel<T, kHasZ, kSoftplus, kArith>;
     const int smem = (int)sizeof(ScanSmem<LC>);
-    static unsigned long long configured = 0;   // per instantiation, one bit per device (the attribute is per device)
+    // per instantiation, one bit per device (the attribute is per device); atomic because autograd calls in from several threads
+    static std::atomic<unsigned long long> configured{0};
     int dev = 0;
     cudaGetDevice(&dev);
-    if (!(configured >> (dev & 63) & 1ull)) {
+    if (!(configured.load(std::memory_order_acquire) >> (dev & 63) & 1ull)) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        configured |= 1ull << (dev & 63);
+        configured.fetch_or(1ull << (dev & 63), std::memory_order_release);
     }
     const int dpg = a.dim / a.n_groups;
     dim3 grid(a.n_groups * ((dpg + kRows - 1) / kRows), batch);

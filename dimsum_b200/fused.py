@@ -221,7 +221,10 @@ class _GateResidualFn(torch.autograd.Function):
         gx = gy if gy.dtype == ctx.x_dtype else gy.to(ctx.x_dtype)
         gm = None
         if ctx.needs_input_grad[2]:
-            gm1 = (gate - 1).contiguous()                          # gy * gate = gy * (1 + (gate - 1)) + 0
+            # gy * gate = gy * (1 + (gate - 1)) + 0.  `gate - 1` is formed in fp32: rounded to bf16 it would quantise the
+            # effective gate to multiples of 2^-8 (a gate of 1e-3 would become 0); the kernel takes the aux dtype
+            # independently of gy's
+            gm1 = (gate.float() - 1).contiguous()
             gm = modulate(gy, torch.zeros_like(gm1), gm1, out_dtype=m.dtype)
         _, ggate = token_colsum(gy, m, want_sum_g=False, out_dtype=gate.dtype)
         return gx, ggate, gm

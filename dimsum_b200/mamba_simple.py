@@ -45,10 +45,13 @@ class Mamba(nn.Module):
         if d_cond is not None:
             # kept for checkpoint compatibility; its output never influences the result
             self.cond_proj = nn.Linear(d_cond, self.d_inner, bias=True, **fk)
-            # the reference returns dcond=None (selective_scan_interface.py:935,1006), so these never receive a gradient;
-            # frozen here so that DDP (find_unused_parameters=False, train.py:180) does not wait for them
-            for prm in self.cond_proj.parameters():
-                prm.requires_grad_(False)
+            # the reference returns dcond=None (selective_scan_interface.py:935,1006), so these never receive a gradient.
+            # They stay trainable by default, exactly like the reference (optimizer parameter lists and AdamW state
+            # index one-to-one); `freeze_dead_cond_proj=True` (tools/train_step.py) freezes them so that DDP with
+            # find_unused_parameters=False does not wait for gradients that never come
+            if kwargs.get("freeze_dead_cond_proj", False):
+                for prm in self.cond_proj.parameters():
+                    prm.requires_grad_(False)
         # dt_proj keeps the variance of delta at init; its bias is softplus^-1 of a log-uniform step in [dt_min, dt_max]
         std = self.dt_rank ** -0.5 * dt_scale
         if dt_init == "constant":
@@ -79,8 +82,10 @@ class Mamba(nn.Module):
         position k reads token table[k]; None for scan_type "none"."""
         if not self.scan_type.startswith(("zigma", "sweep", "jpeg")):
             return None
-        key = (self.layer_idx, device)
+        # keyed on the buffer's storage and version: load_state_dict / .to() after a first forward must not leave a stale table
+        key = (self.layer_idx, device, self.zigzag_paths.data_ptr(), self.zigzag_paths._version)
         if key not in self._order_cache:
+            self._order_cache.clear()
             self._order_cache[key] = self.zigzag_paths[self.layer_idx].to(device=device, dtype=torch.int32).contiguous()
         return self._order_cache[key]
 
@@ -128,11 +133,24 @@ class Mamba(nn.Module):
             return False
         if torch.is_grad_enabled() and self.A_log.requires_grad:
             return False      # training: A changes every optimizer step, the check would cost one host sync per mixer per step
-        key = (self.A_log._version, A.device)
+        # `.data` writes and parameter swaps (EMA / FSDP helpers) do not bump _version: key on the storage as well, and
+        # `invalidate_caches()` is there for in-place `.data.copy_()` updates.  The check is a host sync: call the mixer once
+        # before capturing it into a CUDA graph (GraphedCfgStep warms up first).
+        key = (self.A_log._version, self.A_log.data_ptr(), A.device)
         if key != self._arith_key:
             self._arith_flag = selective_scan_cuda.rows_are_arithmetic(A)
             self._arith_key = key
         return self._arith_flag
+
+    def invalidate_caches(self):
+        """Forget the cached scan tables and the init-form flag of A (call after writing parameters through `.data`)."""
+        self._order_cache.clear()
+        self.__dict__.pop("_block_order_cache", None)
+        self._arith_key, self._arith_flag = None, False
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        super()._load_from_state_dict(*args, **kwargs)
+        self.invalidate_caches()
 
     def _mix(self, hidden_states, order):
         batch, seqlen, _ = hidden_states.shape

@@ -183,12 +183,15 @@ class GatedMLP(nn.Module):
         self.w12 = nn.Linear(in_features, 2 * hidden_features, bias=bias)
         self.w3 = nn.Linear(hidden_features, in_features, bias=bias)
         self.act_layer = act_layer()
+        # the one-pass kernels hard-wire tanh-GELU (mlp.py:65-70 with the released act_layer); any other activation runs
+        # the plain PyTorch expression in eval and in training alike
+        self._tanh_gelu = isinstance(self.act_layer, nn.GELU) and self.act_layer.approximate == "tanh"
 
     def forward(self, x):
         x12 = self.w12(x)
-        if _fused_ok(x12) and x12.dtype in (torch.float32, torch.bfloat16, torch.float16):
+        if self._tanh_gelu and _fused_ok(x12) and x12.dtype in (torch.float32, torch.bfloat16, torch.float16):
             return self.w3(fused.gelu_mul(x12))
-        if _train_fused_ok(x12) and isinstance(self.act_layer, nn.GELU) and self.act_layer.approximate == "tanh":
+        if self._tanh_gelu and _train_fused_ok(x12):
             return self.w3(fused.gelu_mul_fn(x12))
         x1, x2 = x12.chunk(2, dim=-1)
         return self.w3(self.act_layer(x1) * x2)
@@ -219,7 +222,8 @@ def _block_order(mixer, order, inv, device):
     table = mixer.table_order(device) if hasattr(mixer, "table_order") else None
     if table is None:
         return order, inv
-    key = (device, None if order is None else order.data_ptr())
+    # keyed on the table's storage and version too: load_state_dict after a first forward overwrites zigzag_paths in place
+    key = (device, None if order is None else order.data_ptr(), table.data_ptr(), table._version)
     cache = mixer.__dict__.setdefault("_block_order_cache", {})
     if key not in cache:
         total = table if order is None else order[table.long()].contiguous()

@@ -9,7 +9,9 @@ as the closed form of `ref_ops.wavelet_packet_oracle`, and the Mamba slow path (
 tests/test_oracle_golden.py::test_model_oracle_matches_reference (tests/golden/model_*.npz).
 
 Used as (a) the model-level checker for the GPU tests and smoke(), (b) the timed CPU baseline / `--impl reference`
-arm of bench.py.  Never imported by the product package.
+arm of bench.py.  Never imported by the product package.  Every function is device-agnostic torch code: fed CUDA tensors
+it is the "same-device oracle" of SURVEY.md section 8c (reference ops as ordinary CUDA tensor ops, GEMMs identical on both
+sides), which is what tests/test_model_fullsize_gpu.py uses for the DiM-L/2-sized comparisons.
 """
 import math
 
@@ -68,7 +70,7 @@ def dim_forward_oracle(sd, x, t, y, depth=None, attn_every=4, in_channels=4, pat
     depth = depth if depth is not None else 1 + max(int(k.split(".")[1]) for k in sd if k.startswith("blocks."))
     # embedders (models_dim.py:1808-1814)
     half = 128
-    freqs = torch.exp(-math.log(10000) * torch.arange(half, dtype=torch.float32) / half)
+    freqs = torch.exp(-math.log(10000) * torch.arange(half, dtype=torch.float32, device=t.device) / half)
     args = t[:, None].float() * freqs[None]
     temb = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
     c = _lin(sd, "t_embedder.mlp.2", F.silu(_lin(sd, "t_embedder.mlp.0", temb))) + sd["y_embedder.embedding_table.weight"][y]
@@ -83,8 +85,9 @@ def dim_forward_oracle(sd, x, t, y, depth=None, attn_every=4, in_channels=4, pat
         h, residual = ref_ops.rms_norm_oracle(h, sd[p + ".norm.weight"], residual=residual, eps=1e-5, prenorm=True)
         x1, x2 = h.chunk(2, dim=2)
         # spatial branch: materialised order copies exactly like DiMBlockRaw.forward
-        seq = torch.from_numpy(orders.implicit_spatial_order(grid, transpose, reverse))
-        inv = torch.from_numpy(orders.invert(seq.numpy()))
+        seq_np = orders.implicit_spatial_order(grid, transpose, reverse)
+        seq = torch.from_numpy(seq_np).to(h.device)
+        inv = torch.from_numpy(orders.invert(seq_np)).to(h.device)
         s = x1[:, seq]
         sh, sc, g = _adaln(sd, p + ".spatial_mamba", c, 3)
         s = s + g.unsqueeze(1) * _mamba_slow_path(sd, p + ".spatial_mamba.mixer", _modulate(s, sh, sc))
@@ -132,8 +135,8 @@ def euler_sample_oracle(sd, z, y, cfg_scale, num_steps=250, null_class=1000, **k
     sample_ddp.py:168-178."""
     x = torch.cat([z, z], dim=0)
     yy = torch.cat([y, torch.full_like(y, null_class)], dim=0)
-    ts = torch.linspace(0, 1, num_steps)
+    ts = torch.linspace(0, 1, num_steps, device=z.device)
     for i in range(num_steps - 1):
-        v = dim_forward_with_cfg_oracle(sd, x, torch.ones(x.shape[0]) * ts[i], yy, cfg_scale, **kw)
+        v = dim_forward_with_cfg_oracle(sd, x, torch.ones(x.shape[0], device=z.device) * ts[i], yy, cfg_scale, **kw)
         x = x + (ts[i + 1] - ts[i]) * v
     return x[: len(z)]

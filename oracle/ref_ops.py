@@ -196,11 +196,11 @@ def wavelet_packet_inverse_oracle(x):
 def window_scan_oracle(x, w, column_first):
     """`local_scan`, dimsum/scanning_orders.py:347-367 (grid divisible by w, no flip)."""
     grid = int(math.isqrt(x.shape[1]))
-    return x[:, torch.from_numpy(orders.window_order(grid, w, column_first)), :]
+    return x[:, torch.from_numpy(orders.window_order(grid, w, column_first)).to(x.device), :]
 
 
 def window_unscan_oracle(x, w, column_first):
     """`local_reverse`, dimsum/scanning_orders.py:393-416."""
     grid = int(math.isqrt(x.shape[1]))
     inv = orders.invert(orders.window_order(grid, w, column_first))
-    return x[:, torch.from_numpy(inv), :]
+    return x[:, torch.from_numpy(inv).to(x.device), :]

@@ -1,4 +1,6 @@
 """GPU parity of the inference glue kernels (modulate / gated residual with folded token order, add + RMSNorm)."""
+import math
+
 import pytest
 import torch
 
@@ -185,3 +187,29 @@ def test_add_rmsnorm_fn_gradients_match_autograd(x_dtype, C, with_res):
             continue
         assert a.dtype == b.dtype and a.shape == b.shape, name
         assert rel_err(a, b) <= (2e-2 if low and name in ("y", "dx") else 1e-2 if low else 3e-5), (name, rel_err(a, b))
+
+
+@pytest.mark.parametrize("x_dtype", [torch.float32, torch.bfloat16])
+def test_gate_residual_fn_small_bf16_gates_keep_their_gradient(x_dtype):
+    """adaLN gates under bf16 autocast are bf16 and small (zero-initialised, |gate| ~ 1e-3 .. 5e-2 early in training).  The
+    backward computes gy * gate as gy * (1 + (gate - 1)); `gate - 1` must not be rounded to bf16 (spacing 2^-8 near -1), or
+    the gradient into the mixer / MLP branch is quantised to multiples of 0.0039 -- zero for |gate| < 2e-3.  Checked per
+    element, relative to the exact gy * gate, over gates spanning [1e-4, 5e-2] of both signs."""
+    from dimsum_b200 import fused
+    B, L, C = 2, 16, 256
+    g = torch.Generator(device="cuda").manual_seed(21)
+    mags = torch.logspace(-4, math.log10(5e-2), C, device="cuda")
+    signs = torch.where(torch.arange(C, device="cuda") % 2 == 0, 1.0, -1.0)
+    gate = (mags * signs).expand(B, C).to(torch.bfloat16).contiguous().requires_grad_(True)
+    x = torch.randn(B, L, C, generator=g, device="cuda").to(x_dtype).requires_grad_(True)
+    m = torch.randn(B, L, C, generator=g, device="cuda").to(torch.bfloat16).requires_grad_(True)
+    y = fused.gate_residual_fn(x, gate, m)
+    gy = (1.0 + torch.rand(y.shape, generator=g, device="cuda")).to(y.dtype)          # magnitudes in [1, 2): no tiny denominators
+    y.backward(gy)
+    want = gy.float() * gate.detach().float().unsqueeze(1)                            # exact product of the stored values
+    rel = ((m.grad.float() - want).abs() / want.abs()).max().item()
+    assert rel <= 2 ** -7, rel                                                       # one bf16 rounding of the result (2^-8) + slack
+    assert torch.count_nonzero(m.grad) == m.grad.numel()
+    want_gate = (gy.float() * m.detach().float()).sum(1)
+    assert rel_err(gate.grad, want_gate) <= 1e-2
+    assert rel_err(x.grad, gy) <= 1e-6
