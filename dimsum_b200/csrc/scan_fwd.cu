@@ -19,6 +19,7 @@
 //     are the powers r, r^2, .. r^16 of ONE exp (kArith): 1 MUFU + 8 packed multiplies instead of 16 MUFU.  Moving
 //     part of the exps to a polynomial on the FMA pipe was measured and is slower (profiles/r1_scan_fwd_experiments.md).
 #include <atomic>
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
@@ -26,7 +27,7 @@
 namespace dimsum {
 namespace {
 
-constexpr int kRows = 128;          // threads per CTA == channel rows per CTA
+// threads per CTA == channel rows per CTA: 128, or 64 for single-wave grids that balance better in finer pieces
 constexpr int kNS = 16;             // padded state count
 constexpr int kBCPitch = 20;        // words: 16 states + pad -> conflict-free transposed STS.128, aligned LDS.128
 constexpr int kRowBytes = 64;       // payload bytes per tile row per chunk
@@ -40,10 +41,10 @@ struct ScanFwdArgs {
     const int32_t *perm;
     int64_t u_bs, u_ds, dl_bs, dl_ds, z_bs, z_ds, out_bs, out_ds, oz_bs, oz_ds;
     int64_t A_ds, A_ns, B_bs, B_gs, B_ns, C_bs, C_gs, C_ns;
-    int dim, seqlen, dstate, n_groups, n_chunks, softplus, vec_io;
+    int dim, seqlen, dstate, n_groups, n_chunks, softplus, vec_io, half_exp;
 };
 
-template <int LC>
+template <int LC, int kRows>
 struct ScanSmem {
     unsigned char u[2][kRows][kRowPitch];
     unsigned char dl[2][kRows][kRowPitch];
@@ -96,13 +97,16 @@ DEV void store_last_state(const ScanFwdArgs &a, int b, int d, const float2 (&h2)
     }
 }
 
-template <typename T, bool kHasZ, bool kSoftplus, bool kArith>
-__global__ void __launch_bounds__(kRows, sizeof(T) == 4 ? 4 : 3) scan_fwd_kernel(const ScanFwdArgs a) {
+// kHalfExp (16-bit I/O only, experiment behind DIMSUM_SCAN_EX2_F16X2=1): decays from ex2.approx.ftz.f16x2, two per MUFU issue.
+// Measured and NOT the default: see profiles/r2_scan_fwd_experiments.md (an f16 decay has 11 significant bits, so a slow
+// state a = 0.999 is quantised to 0.9990 / 0.9995 and its memory length is off by tens of percent).
+template <typename T, bool kHasZ, bool kSoftplus, bool kArith, int kRows, bool kHalfExp = false>
+__global__ void __launch_bounds__(kRows, (sizeof(T) == 4 ? 4 : 3) * (128 / kRows)) scan_fwd_kernel(const ScanFwdArgs a) {
     constexpr int VEC = Io<T>::kVec;                 // elements per 16 bytes
     constexpr int LC = kRowBytes / (int)sizeof(T);   // steps per chunk: 16 (fp32) / 32 (16-bit)
     constexpr int VPR = kRowBytes / 16;              // 16-byte vectors per tile row = 4
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    ScanSmem<LC> &s = *reinterpret_cast<ScanSmem<LC> *>(smem_raw);
+    ScanSmem<LC, kRows> &s = *reinterpret_cast<ScanSmem<LC, kRows> *>(smem_raw);
 
     const int tid = threadIdx.x;
     const int b = blockIdx.y;
@@ -181,25 +185,32 @@ __global__ void __launch_bounds__(kRows, sizeof(T) == 4 ? 4 : 3) scan_fwd_kernel
         }
         cp_async_commit();
     };
-    // B / C chunk through registers: thread = (l = tid % LC, state quad = tid / LC)
-    constexpr bool kBCAll = (LC * (kNS / 4) >= kRows);   // every thread participates (LC = 32)
-    const int bc_l = tid % LC, bc_q = tid / LC;
-    const bool bc_on = kBCAll || tid < LC * (kNS / 4);
-    float bq[4], cq[4];
+    // B / C chunk through registers: item = (l = item % LC, state quad = item / LC), LC * 4 items over kRows threads
+    constexpr int kBCItems = LC * (kNS / 4);
+    constexpr int kBCIter = (kBCItems + kRows - 1) / kRows;
+    float bq[kBCIter][4], cq[kBCIter][4];
     auto load_bc = [&](int c) {
-        const int l = c * LC + bc_l;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int n = bc_q * 4 + i;
-            const bool ok = bc_on && n < a.dstate && l < L;
-            bq[i] = ok ? Io<T>::ld(Bg + n * a.B_ns + l) : 0.f;
-            cq[i] = ok ? Io<T>::ld(Cg + n * a.C_ns + l) : 0.f;
+        for (int it = 0; it < kBCIter; ++it) {
+            const int item = tid + it * kRows;
+            const int l = c * LC + item % LC, q = item / LC;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int n = q * 4 + i;
+                const bool ok = item < kBCItems && n < a.dstate && l < L;
+                bq[it][i] = ok ? Io<T>::ld(Bg + n * a.B_ns + l) : 0.f;
+                cq[it][i] = ok ? Io<T>::ld(Cg + n * a.C_ns + l) : 0.f;
+            }
         }
     };
     auto store_bc = [&](int st) {
-        if (bc_on) {
-            *reinterpret_cast<float4 *>(&s.Bs[st][bc_l][bc_q * 4]) = make_float4(bq[0], bq[1], bq[2], bq[3]);
-            *reinterpret_cast<float4 *>(&s.Cs[st][bc_l][bc_q * 4]) = make_float4(cq[0], cq[1], cq[2], cq[3]);
+#pragma unroll
+        for (int it = 0; it < kBCIter; ++it) {
+            const int item = tid + it * kRows;
+            if (item < kBCItems) {
+                *reinterpret_cast<float4 *>(&s.Bs[st][item % LC][(item / LC) * 4]) = make_float4(bq[it][0], bq[it][1], bq[it][2], bq[it][3]);
+                *reinterpret_cast<float4 *>(&s.Cs[st][item % LC][(item / LC) * 4]) = make_float4(cq[it][0], cq[it][1], cq[it][2], cq[it][3]);
+            }
         }
     };
 
@@ -249,6 +260,18 @@ __global__ void __launch_bounds__(kRows, sizeof(T) == 4 ? 4 : 3) scan_fwd_kernel
                     dec[0] = make_float2(r, r2);
 #pragma unroll
                     for (int p = 1; p < kNS / 2; ++p) dec[p] = mul2(dec[p - 1], splat2(r2));
+                } else if (kHalfExp) {
+#pragma unroll
+                    for (int p = 0; p < kNS / 2; ++p) {
+                        const float2 t = mul2(splat2(dlt), A2[p]);
+                        uint32_t hx, he;
+                        asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hx) : "f"(t.y), "f"(t.x));
+                        asm("ex2.approx.f16x2 %0, %1;" : "=r"(he) : "r"(hx));
+                        float lo, hi;
+                        asm("{\n\t.reg .f16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}"
+                            : "=f"(lo), "=f"(hi) : "r"(he));
+                        dec[p] = make_float2(lo, hi);
+                    }
                 } else {
 #pragma unroll
                     for (int p = 0; p < kNS / 2; ++p) {
@@ -329,11 +352,11 @@ __global__ void __launch_bounds__(kRows, sizeof(T) == 4 ? 4 : 3) scan_fwd_kernel
     if (a.x != nullptr && row_ok) store_last_state(a, b, d0 + tid, h2);
 }
 
-template <typename T, bool kHasZ, bool kSoftplus, bool kArith>
-int launch(const ScanFwdArgs &a, int batch, cudaStream_t stream) {
+template <typename T, bool kHasZ, bool kSoftplus, bool kArith, int kRows, bool kHalfExp = false>
+int launch_rows(const ScanFwdArgs &a, int batch, cudaStream_t stream) {
     constexpr int LC = kRowBytes / (int)sizeof(T);
-    auto kern = scan_fwd_kernel<T, kHasZ, kSoftplus, kArith>;
-    const int smem = (int)sizeof(ScanSmem<LC>);
+    auto kern = scan_fwd_kernel<T, kHasZ, kSoftplus, kArith, kRows, kHalfExp>;
+    const int smem = (int)sizeof(ScanSmem<LC, kRows>);
     // per instantiation, one bit per device (the attribute is per device); atomic because autograd calls in from several threads
     static std::atomic<unsigned long long> configured{0};
     int dev = 0;
@@ -346,6 +369,48 @@ int launch(const ScanFwdArgs &a, int batch, cudaStream_t stream) {
     dim3 grid(a.n_groups * ((dpg + kRows - 1) / kRows), batch);
     kern<<<grid, kRows, smem, stream>>>(a);
     return check_launch("selective_scan_fwd");
+}
+
+// Fraction of the machine a grid of n CTAs keeps busy when `per_sm` of them fit on each of `sms` SMs: a single wave is
+// limited by the fullest SM, several waves by the last, partial one.
+inline double wave_efficiency(long long n, int sms, int per_sm) {
+    if (n <= (long long)sms * per_sm) {
+        const double per = (double)n / sms;
+        return per / (double)((n + sms - 1) / sms);
+    }
+    const double waves = (double)n / ((double)sms * per_sm);
+    return waves / (double)(long long)(waves + 0.999999);
+}
+
+template <typename T, bool kHasZ, bool kSoftplus, bool kArith>
+int launch(const ScanFwdArgs &a, int batch, cudaStream_t stream) {
+    // 128-row CTAs share one B/C tile among 128 channels; 64-row CTAs cost twice the B/C staging per channel but cut a
+    // single-wave grid into finer pieces (64 latents x 1024 channels: 512 CTAs leave SMs with 3 or 4 -> 86 % busy; 1024
+    // half-height CTAs leave them with 6 or 7 -> 99 %).  DIMSUM_SCAN_ROWS=128|64 pins the choice.
+    static std::atomic<int> sms_cached{0};
+    static std::atomic<int> forced_cached{-1};
+    int sms = sms_cached.load(std::memory_order_relaxed);
+    if (sms == 0) {
+        int dev = 0, v = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        const char *e = getenv("DIMSUM_SCAN_ROWS");
+        forced_cached.store(e ? atoi(e) : 0, std::memory_order_relaxed);
+        sms = v > 0 ? v : 148;
+        sms_cached.store(sms, std::memory_order_relaxed);
+    }
+    const int forced = forced_cached.load(std::memory_order_relaxed);
+    const int dpg = a.dim / a.n_groups;
+    const int per128 = sizeof(T) == 4 ? 4 : 3;
+    const long long n128 = (long long)a.n_groups * ((dpg + 127) / 128) * batch, n64 = (long long)a.n_groups * ((dpg + 63) / 64) * batch;
+    bool half = wave_efficiency(n64, sms, 2 * per128) > wave_efficiency(n128, sms, per128) + 0.04;
+    if (forced == 64) half = true;
+    if (forced == 128) half = false;
+    if constexpr (sizeof(T) == 2 && !kArith && kHasZ && kSoftplus) {      // experiment hook, see kHalfExp
+        if (a.half_exp) return launch_rows<T, kHasZ, kSoftplus, kArith, 128, true>(a, batch, stream);
+    }
+    return half ? launch_rows<T, kHasZ, kSoftplus, kArith, 64>(a, batch, stream)
+                : launch_rows<T, kHasZ, kSoftplus, kArith, 128>(a, batch, stream);
 }
 
 template <typename T, bool kArith>
@@ -410,6 +475,10 @@ extern "C" int dimsum_selective_scan_fwd(const dimsum_scan_fwd_params *p, void *
     a.dim = (int)p->dim; a.seqlen = (int)p->seqlen; a.dstate = (int)p->dstate; a.n_groups = (int)p->n_groups;
     a.n_chunks = (int)p->n_chunks;
     a.softplus = p->delta_softplus != 0;
+    {
+        static const int half_exp_env = [] { const char *e = getenv("DIMSUM_SCAN_EX2_F16X2"); return e ? atoi(e) : 0; }();
+        a.half_exp = half_exp_env;
+    }
 
     const int esz = p->io_dtype == DIMSUM_F32 ? 4 : 2;
     const int vec = 16 / esz;

@@ -49,7 +49,9 @@ def test_selective_scan_forward_and_all_grads_at_config2_width(dtype, L):
         grads = torch.autograd.grad(out, leaves, dout.to(dev))
         return out, last, grads
 
-    want, want_last, want_g = run(ref_ops.selective_scan_oracle, "cpu")
+    # L=256: CPU oracle (root of trust).  L=1024: the same oracle fed CUDA tensors (SURVEY.md 8c "same-device oracle") -- autograd
+    # through 1024 sequential CPU steps of (8, 2048, 16) tensors takes minutes
+    want, want_last, want_g = run(ref_ops.selective_scan_oracle, "cpu" if L <= 256 else "cuda")
     got, got_last, got_g = run(selective_scan_fn, "cuda")
     t = tol(dtype)
     assert got.dtype == dtype and rel_err(got, want) <= t, rel_err(got, want)

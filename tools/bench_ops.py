@@ -46,6 +46,9 @@ def main():
     ap.add_argument("--json", default=None)
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--bwd", action="store_true", help="time the backward kernels at every shape (default: R <= 64)")
+    ap.add_argument("--shapes", default=None, help="comma-separated RxDxL list replacing the default scan / conv shapes")
+    ap.add_argument("--scan-only", action="store_true", help="only the scan / conv rows (skip wavelet, glue and gather kernels)")
+    ap.add_argument("--tag", default="", help="free text appended to every printed row (experiment label)")
     args = ap.parse_args()
     from dimsum_b200 import causal_conv1d_cuda, selective_scan_cuda, wavelet_packet, scanning_orders as so
     pk = peak()
@@ -55,6 +58,8 @@ def main():
     shapes = [(256, 2048, 256), (64, 2048, 256), (8, 2048, 256), (512, 1024, 256), (128, 1024, 1024)]
     if args.quick:
         shapes = shapes[:1]
+    if args.shapes:
+        shapes = [tuple(int(v) for v in item.split("x")) for item in args.shapes.split(",")]
     for dtype in (torch.float32, torch.bfloat16):
         s = 4 if dtype == torch.float32 else 2
         for (R, D, L) in shapes:
@@ -102,6 +107,8 @@ def main():
                                  frac=by_cb / med / 1e6 / pk))
                 del out, xck, out_z, dout
             del xz, u, z, delta, Bm, Cm
+        if args.scan_only:
+            continue
         # wavelet at the model shape: 512 rows, 16x16 tokens, 512 channels
         x = torch.randn(512, 256, 512, device="cuda").to(dtype)
         pos = so.as_index(so.reverse_permut_np(so.window_order(16, 4, False)), "cuda")
@@ -163,7 +170,7 @@ def main():
         del xz, u, delta, Bm, Cm
     for r in rows:
         print(f"{r['op']:20s} {r['dtype']:15s} R={r['R']:4d} D={r['D']:5d} L={r['L']:5d}  {r['ms']:8.3f} ms (best {r['ms_best']:.3f})"
-              f"  {r['gbs']:8.1f} GB/s  {100 * r['frac']:5.1f}% of measured peak {pk:.0f}")
+              f"  {r['gbs']:8.1f} GB/s  {100 * r['frac']:5.1f}% of measured peak {pk:.0f} {args.tag}")
     if args.json:
         json.dump(rows, open(args.json, "w"), indent=1)
 
