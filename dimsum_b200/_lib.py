@@ -108,6 +108,7 @@ ScanFwdParams = STRUCTS["dimsum_scan_fwd_params"]
 ScanBwdParams = STRUCTS["dimsum_scan_bwd_params"]
 ConvFwdParams = STRUCTS["dimsum_conv_fwd_params"]
 ConvBwdParams = STRUCTS["dimsum_conv_bwd_params"]
+ConvXprojParams = STRUCTS["dimsum_conv_xproj_params"]
 GatherParams = STRUCTS["dimsum_gather_params"]
 WaveletParams = STRUCTS["dimsum_wavelet_params"]
 RowwiseParams = STRUCTS["dimsum_rowwise_params"]
@@ -123,6 +124,7 @@ ENTRY_POINTS = {
     "dimsum_selective_scan_bwd": ScanBwdParams,
     "dimsum_causal_conv1d_fwd": ConvFwdParams,
     "dimsum_causal_conv1d_bwd": ConvBwdParams,
+    "dimsum_conv_xproj_fwd": ConvXprojParams,
     "dimsum_token_gather": GatherParams,
     "dimsum_wavelet_packet_fwd": WaveletParams,
     "dimsum_wavelet_packet_inv": WaveletParams,

@@ -76,6 +76,69 @@ def causal_conv1d_fwd_cond(x, weight, bias_, silu_activation, init_x):
     return _fwd_into(x, weight, bias_, silu_activation, init_x)
 
 
+def conv_xproj_supported(x, weight, x_proj_weight, out=None):
+    """Shapes / layouts the fused conv + x_proj kernel takes (anything else runs the two separate steps)."""
+    if x.dtype not in _DT or x_proj_weight.dtype != x.dtype or not x.is_cuda or x.dim() != 3 or x.stride(2) != 1:
+        return False
+    es = x.element_size()
+    vec, kc = 16 // es, 128 // es
+    if out is not None and not (out.dtype == x.dtype and out.is_cuda and out.shape == x.shape and out.stride(2) == 1
+                                and out.stride(0) % vec == 0 and out.stride(1) % vec == 0 and out.data_ptr() % 16 == 0):
+        return False
+    n_out, dim = x_proj_weight.shape
+    return (dim == x.shape[1] and dim % kc == 0 and x.shape[2] % vec == 0 and 8 <= n_out <= 256 and n_out % 8 == 0
+            and x_proj_weight.stride(1) == 1 and x_proj_weight.stride(0) % vec == 0 and x_proj_weight.data_ptr() % 16 == 0
+            and x.stride(0) % vec == 0 and x.stride(1) % vec == 0 and x.data_ptr() % 16 == 0 and 2 <= weight.shape[1] <= 4
+            and x.shape[0] <= 65535)
+
+
+def conv_xproj_fwd(x, weight, bias_, x_proj_weight, precise=False, out=None, split=None):
+    """u = silu(causal_conv1d(x)) and x_dbl = x_proj(u) in ONE tcgen05 kernel (selective_scan_interface.py:836-840 fused).
+
+    -> (u, x_dbl) with x_dbl (batch, n_out, seqlen) channel-major, or, with `split` = dt_rank (a multiple of 8),
+    -> (u, dt, bc): dt (split, batch * seqlen) -- the right operand of the dt_proj GEMM, so delta = (W_dt @ dt) comes out in
+    the (dim, batch, seqlen) layout of selective_scan_interface.py:841 -- and bc (batch, n_out - split, seqlen), whose halves
+    are B and C in the layout the scan reads (no rearrange copies).
+    `out` (the reference's `init_states` buffer, causal_conv1d.cpp:326) receives u when given.  `precise` selects the
+    3xTF32 split for fp32 I/O (fp32-grade results, used when TF32 matmuls are disabled)."""
+    batch, dim, seqlen, width = _checks(x, weight, bias_)
+    _check(conv_xproj_supported(x, weight, x_proj_weight), "conv_xproj_fwd: unsupported shape or layout (see conv_xproj_supported)")
+    vec = 16 // x.element_size()
+    if out is not None:
+        _check(out.dtype == x.dtype and out.is_cuda and out.shape == x.shape and out.stride(2) == 1
+               and out.stride(0) % vec == 0 and out.stride(1) % vec == 0 and out.data_ptr() % 16 == 0,
+               "conv_xproj_fwd: out must match x in dtype and shape with 16-byte aligned rows")
+    n_out = x_proj_weight.shape[0]
+    if split is not None:
+        _check(0 < split < n_out and split % 8 == 0, "conv_xproj_fwd: split must be a multiple of 8 inside (0, n_out)")
+    with torch.cuda.device(x.device):
+        u = out if out is not None else torch.empty(x.shape, device=x.device, dtype=x.dtype)
+        p = _lib.ConvXprojParams()
+        p.batch, p.dim, p.seqlen, p.width, p.n_out = batch, dim, seqlen, width, n_out
+        p.io_dtype, p.w_dtype, p.precision = _DT[x.dtype], _DT[weight.dtype], int(bool(precise) and x.dtype == torch.float32)
+        p.x_batch_stride, p.x_d_stride = x.stride(0), x.stride(1)
+        p.u_batch_stride, p.u_d_stride = u.stride(0), u.stride(1)
+        if split is None:
+            x_dbl = torch.empty((batch, n_out, seqlen), device=x.device, dtype=x.dtype)
+            p.x_dbl_batch_stride, p.x_dbl_row_stride = x_dbl.stride(0), x_dbl.stride(1)
+            p.x_dbl = x_dbl.data_ptr()
+            result = (u, x_dbl)
+        else:
+            dt = torch.empty((split, batch * seqlen), device=x.device, dtype=x.dtype)
+            bc = torch.empty((batch, n_out - split, seqlen), device=x.device, dtype=x.dtype)
+            p.split_rows = split
+            p.x_dbl_batch_stride, p.x_dbl_row_stride = seqlen, batch * seqlen
+            p.tail_batch_stride, p.tail_row_stride = bc.stride(0), bc.stride(1)
+            p.x_dbl, p.x_dbl_tail = dt.data_ptr(), bc.data_ptr()
+            result = (u, dt, bc)
+        p.w_d_stride, p.w_width_stride, p.xw_row_stride = weight.stride(0), weight.stride(1), x_proj_weight.stride(0)
+        p.x, p.conv_weight, p.x_proj_weight = x.data_ptr(), weight.data_ptr(), x_proj_weight.data_ptr()
+        p.conv_bias = bias_.data_ptr() if bias_ is not None else None
+        p.u = u.data_ptr()
+        _lib.call("dimsum_conv_xproj_fwd", p, _stream(x))
+    return result
+
+
 def causal_conv1d_bwd(x, weight, bias_, dout, dx_, silu_activation):
     """causal_conv1d.cpp:349-427 -> [dx, dweight, dbias]."""
     batch, dim, seqlen, width = _checks(x, weight, bias_)

@@ -6,10 +6,17 @@ Everything runs on the sm_100a kernels behind the C-ABI; there is no PyTorch or 
 is not recording (sampling) the scan skips the pre-gate `out` and checkpoint stores, which is the
 "inference" byte count of SURVEY.md section 8d.
 """
+import os
+
 import torch
 import torch.nn.functional as F
 
 from . import causal_conv1d_cuda, selective_scan_cuda
+
+
+def fused_xproj_enabled():
+    """DIMSUM_FUSED_XPROJ=0 runs conv and x_proj as two steps (the round-1 path), for A/B measurements."""
+    return os.environ.get("DIMSUM_FUSED_XPROJ", "1") != "0"
 
 
 def _last_contig(t):
@@ -110,19 +117,30 @@ class MambaInnerFn(torch.autograd.Function):
         conv_w = conv1d_weight.reshape(conv1d_weight.shape[0], conv1d_weight.shape[-1])
         x, z = xz.chunk(2, dim=1)
         conv1d_bias = conv1d_bias.contiguous() if conv1d_bias is not None else None
-        conv_out = causal_conv1d_cuda.causal_conv1d_fwd_cond(x, conv_w, conv1d_bias, True, init_states)
-        R, Dm = conv_out.shape[0], conv_out.shape[1]
+        R, Dm = x.shape[0], x.shape[1]
+        if (fused_xproj_enabled() and B_proj_bias is None and C_proj_bias is None and rank % 8 == 0
+                and causal_conv1d_cuda.conv_xproj_supported(x, conv_w, x_proj_weight, out=init_states)):
+            # conv + SiLU fused in front of the x_proj contraction (tcgen05): one pass over x writes u once and emits dt
+            # as the (rank, R*L) operand of the dt_proj GEMM and B / C in the scan's layout -- no second read of u, no
+            # rearrange copies (selective_scan_interface.py:836-866 in one kernel)
+            precise = x.dtype == torch.float32 and not torch.backends.cuda.matmul.allow_tf32
+            conv_out, dt2d, bc = causal_conv1d_cuda.conv_xproj_fwd(x, conv_w, conv1d_bias, x_proj_weight, precise,
+                                                                   out=init_states, split=rank)
+            Bm, Cm = bc[:, :N].unsqueeze(1), bc[:, N:].unsqueeze(1)
+        else:
+            conv_out = causal_conv1d_cuda.causal_conv1d_fwd_cond(x, conv_w, conv1d_bias, True, init_states)
+            x_dbl = _rows_times_wt(conv_out, x_proj_weight).reshape(R * L, -1)
+            dt2d = x_dbl[:, :rank].t()                                   # (rank, R*L) view
+            Bm = x_dbl[:, rank:rank + N]
+            Cm = x_dbl[:, rank + N:]
+            if B_proj_bias is not None:
+                Bm = Bm + B_proj_bias.to(Bm.dtype)
+            if C_proj_bias is not None:
+                Cm = Cm + C_proj_bias.to(Cm.dtype)
+            Bm = Bm.view(R, L, 1, N).permute(0, 2, 3, 1).contiguous()
+            Cm = Cm.view(R, L, 1, N).permute(0, 2, 3, 1).contiguous()
         # delta keeps d slowest / l fastest, the layout the scan wants (selective_scan_interface.py:837-841)
-        x_dbl = _rows_times_wt(conv_out, x_proj_weight).reshape(R * L, -1)
-        delta = (delta_proj_weight @ x_dbl[:, :rank].t()).view(Dm, R, L).transpose(0, 1)
-        Bm = x_dbl[:, rank:rank + N]
-        Cm = x_dbl[:, rank + N:]
-        if B_proj_bias is not None:
-            Bm = Bm + B_proj_bias.to(Bm.dtype)
-        if C_proj_bias is not None:
-            Cm = Cm + C_proj_bias.to(Cm.dtype)
-        Bm = Bm.view(R, L, 1, N).permute(0, 2, 3, 1).contiguous()
-        Cm = Cm.view(R, L, 1, N).permute(0, 2, 3, 1).contiguous()
+        delta = (delta_proj_weight @ dt2d).view(Dm, R, L).transpose(0, 1)
         D = D.contiguous() if D is not None else None
         needs_grad = recording and any(ctx.needs_input_grad)
         out, x_ckpt, out_z = selective_scan_cuda.fwd(conv_out, delta, A, Bm, Cm, D, z, delta_bias, delta_softplus,
@@ -132,7 +150,7 @@ class MambaInnerFn(torch.autograd.Function):
         ctx.B_bias, ctx.C_bias = B_proj_bias is not None, C_proj_bias is not None
         ctx.out_bias = out_proj_bias is not None
         if needs_grad:  # conv_out and delta are recomputed in backward (checkpoint level 1, :876-877)
-            ctx.save_for_backward(xz, conv_w, conv1d_bias, x_dbl, x_proj_weight, delta_proj_weight, out_proj_weight,
+            ctx.save_for_backward(xz, conv_w, conv1d_bias, dt2d, x_proj_weight, delta_proj_weight, out_proj_weight,
                                   A, Bm, Cm, D, delta_bias, x_ckpt, out)
         if not has_out_proj:
             return out_z
@@ -142,7 +160,7 @@ class MambaInnerFn(torch.autograd.Function):
     @staticmethod
     @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, dout):
-        (xz, conv_w, conv1d_bias, x_dbl, x_proj_weight, delta_proj_weight, out_proj_weight, A, Bm, Cm, D, delta_bias,
+        (xz, conv_w, conv1d_bias, dt2d, x_proj_weight, delta_proj_weight, out_proj_weight, A, Bm, Cm, D, delta_bias,
          x_ckpt, out) = ctx.saved_tensors
         R, twoD, L = xz.shape
         Dm = twoD // 2
@@ -151,7 +169,7 @@ class MambaInnerFn(torch.autograd.Function):
         x, z = xz.chunk(2, dim=1)
         dout = _last_contig(dout)
         conv_out = causal_conv1d_cuda.causal_conv1d_fwd(x, conv_w, conv1d_bias, True)
-        delta = (delta_proj_weight @ x_dbl[:, :rank].t()).view(Dm, R, L).transpose(0, 1)
+        delta = (delta_proj_weight @ dt2d).view(Dm, R, L).transpose(0, 1)
         dxz = torch.empty_like(xz)
         dx, dz = dxz.chunk(2, dim=1)
         if ctx.has_out_proj:
@@ -165,7 +183,7 @@ class MambaInnerFn(torch.autograd.Function):
         if ctx.has_out_proj:
             dout_proj_weight = dout2 @ out_z.transpose(1, 2).reshape(R * L, Dm)
             dout_proj_bias = dout2.sum(dim=1) if ctx.out_bias else None
-        dx_dbl = torch.empty_like(x_dbl)
+        dx_dbl = torch.empty((R * L, rank + 2 * N), device=xz.device, dtype=dt2d.dtype)
         dBf = dB.squeeze(1).transpose(1, 2).reshape(R * L, N)
         dCf = dC.squeeze(1).transpose(1, 2).reshape(R * L, N)
         dx_dbl[:, rank:rank + N] = dBf
@@ -173,7 +191,7 @@ class MambaInnerFn(torch.autograd.Function):
         dB_proj_bias = dBf.sum(0) if ctx.B_bias else None
         dC_proj_bias = dCf.sum(0) if ctx.C_bias else None
         ddelta2 = ddelta.transpose(0, 1).reshape(Dm, R * L)
-        ddelta_proj_weight = ddelta2 @ x_dbl[:, :rank]
+        ddelta_proj_weight = ddelta2 @ dt2d.t()
         dx_dbl[:, :rank] = ddelta2.t() @ delta_proj_weight
         conv_flat = conv_out.transpose(1, 2).reshape(R * L, Dm)
         dx_proj_weight = dx_dbl.t() @ conv_flat

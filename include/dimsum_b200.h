@@ -14,6 +14,8 @@
  *   dimsum_causal_conv1d_fwd    causal_conv1d_fwd() / causal_conv1d_fwd_cond()
  *                               causal-conv1d/csrc/causal_conv1d.cpp:221-281, :283-347 (POD causal_conv1d.h:9-35)
  *   dimsum_causal_conv1d_bwd    causal_conv1d_bwd() / causal_conv1d_bwd_cond()  causal_conv1d.cpp:349-427, :429-510
+ *   dimsum_conv_xproj_fwd       causal_conv1d_fwd[_cond] + the x_proj F.linear + the B / C rearranges of MambaInnerFn*.forward,
+ *                               mamba/mamba_ssm/ops/selective_scan_interface.py:836-866 (one tcgen05 kernel)
  *   dimsum_token_gather         torch.gather on token orders, mamba/mamba_ssm/modules/mamba_simple.py:634,657 and the
  *                               rearrange/flip/local_scan copies of dimsum/models_dim.py:1498-1524, :660-664,:700-701
  *   dimsum_wavelet_packet_fwd   WaveDiMBlock._dwt_fast  dimsum/models_dim.py:572-586 (+ local_scan :662)
@@ -147,6 +149,41 @@ typedef struct {
 } dimsum_conv_bwd_params;
 
 int dimsum_causal_conv1d_bwd(const dimsum_conv_bwd_params *p, void *stream);
+
+/* ---- causal conv1d + SiLU fused in front of the x_proj contraction (tcgen05 tensor cores) ------------------
+ * Replaces the first half of MambaInnerFn*.forward (mamba/mamba_ssm/ops/selective_scan_interface.py:836-866):
+ *     conv1d_out = causal_conv1d_cuda.causal_conv1d_fwd[_cond](x, conv1d_weight, conv1d_bias, True[, init_states])
+ *     x_dbl      = F.linear(rearrange(conv1d_out, "b d l -> (b l) d"), x_proj_weight)
+ *     B, C       = rearrange(x_dbl[:, ...], "(b l) dstate -> b 1 dstate l").contiguous()
+ * x            : (batch, dim, seqlen) io_dtype, sequence stride 1 (the first half of xz)
+ * conv_weight  : (dim, width) w_dtype, conv_bias (dim) w_dtype or NULL; width 2..4; SiLU always applied
+ * x_proj_weight: (n_out, dim) io_dtype, row stride xw_row_stride, n_out = dt_rank + 2*dstate (multiple of 8, <= 256)
+ * u            : (batch, dim, seqlen) io_dtype  = silu(conv(x)), bit-identical to dimsum_causal_conv1d_fwd
+ * x_dbl        : x_proj(u), CHANNEL-major, io_dtype: output row e (< n_out) of batch b, token l is written to
+ *                x_dbl + b * x_dbl_batch_stride + e * x_dbl_row_stride + l for e < split_rows (or all e when x_dbl_tail is
+ *                NULL) and to x_dbl_tail + b * tail_batch_stride + (e - split_rows) * tail_row_stride + l otherwise;
+ *                split_rows is a multiple of 8.  The Python host puts the dt rows in a (dt_rank, batch * seqlen) matrix --
+ *                the right operand of the dt_proj GEMM, selective_scan_interface.py:841 -- and the B / C rows in a
+ *                (batch, 2*dstate, seqlen) tensor whose halves ARE B and C in the layout the scan reads: the two
+ *                rearrange(...).contiguous() copies of :852,:862 disappear
+ * precision    : 0 = one tensor-core pass (TF32 for fp32 I/O -- what cuBLAS does under allow_tf32 -- bf16 / fp16 operands for
+ *                16-bit I/O, fp32 accumulation); 1 = 3xTF32 split for fp32 I/O (fp32-grade, ~1e-6 relative)
+ * Requires dim % (128 / element size) == 0, seqlen % (16 / element size) == 0 and 16-byte aligned rows; anything else
+ * returns DIMSUM_ERR_UNSUPPORTED and the caller runs the two separate steps.
+ */
+typedef struct {
+    int64_t batch, dim, seqlen, width, n_out, split_rows;
+    int64_t io_dtype, w_dtype, precision;
+    int64_t x_batch_stride, x_d_stride;
+    int64_t u_batch_stride, u_d_stride;
+    int64_t x_dbl_batch_stride, x_dbl_row_stride;
+    int64_t tail_batch_stride, tail_row_stride;
+    int64_t w_d_stride, w_width_stride, xw_row_stride;
+    const void *x, *conv_weight, *conv_bias, *x_proj_weight;
+    void *u, *x_dbl, *x_dbl_tail;
+} dimsum_conv_xproj_params;
+
+int dimsum_conv_xproj_fwd(const dimsum_conv_xproj_params *p, void *stream);
 
 /* ---- token-major gather: dst[b, l, :] = src[b, index[l], :]  for (batch, seqlen, channels) rows ---- */
 typedef struct {

@@ -93,6 +93,23 @@ def main():
             med, best = timeit(lambda: causal_conv1d_cuda.causal_conv1d_fwd(u, w, cb, True), flush=flush)
             rows.append(dict(op="conv_fwd", dtype=str(dtype), R=R, D=D, L=L, ms=med, ms_best=best, gbs=by_c / med / 1e6,
                              frac=by_c / med / 1e6 / pk))
+            if D % 64 == 0 and L % 8 == 0:
+                xw = (torch.randn(64, D, generator=g, device="cuda") / D ** 0.5).to(dtype)
+                by_x = 2 * s * R * D * L + s * R * 64 * L + s * 64 * D
+                for tag, precise in (("conv_xproj", False),) + ((("conv_xproj_3xtf32", True),) if dtype == torch.float32 else ()):
+                    med, best = timeit(lambda: causal_conv1d_cuda.conv_xproj_fwd(u, w, cb, xw, precise=precise, split=32), flush=flush)
+                    rows.append(dict(op=tag, dtype=str(dtype), R=R, D=D, L=L, ms=med, ms_best=best, gbs=by_x / med / 1e6,
+                                     frac=by_x / med / 1e6 / pk))
+                # the two-step path it replaces: conv kernel + cuBLAS x_proj + the two B / C rearrange copies
+                def two_step():
+                    cu = causal_conv1d_cuda.causal_conv1d_fwd(u, w, cb, True)
+                    xd = torch.bmm(cu.transpose(1, 2), xw.t().unsqueeze(0).expand(R, -1, -1)).reshape(R * L, -1)
+                    Bc = xd[:, 32:48].view(R, L, 1, N).permute(0, 2, 3, 1).contiguous()
+                    Cc = xd[:, 48:].view(R, L, 1, N).permute(0, 2, 3, 1).contiguous()
+                    return cu, xd, Bc, Cc
+                med, best = timeit(two_step, flush=flush)
+                rows.append(dict(op="conv+xproj_2step", dtype=str(dtype), R=R, D=D, L=L, ms=med, ms_best=best, gbs=by_x / med / 1e6,
+                                 frac=by_x / med / 1e6 / pk))
             if R <= 64 or args.bwd:
                 out, xck, out_z = selective_scan_cuda.fwd(u, delta, A, Bm, Cm, Dv, z, bias, True)
                 dout = torch.randn(R, D, L, generator=g, device="cuda").to(dtype)

@@ -21,8 +21,8 @@ DEV uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared
 // ---- descriptors -------------------------------------------------------------------------------------------------------
 // shared-memory matrix descriptor, no swizzle (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp): start>>4 [0,14), LBO>>4 [16,30),
 // SBO>>4 [32,46), version=1 [46,48), layout_type=0 [61,64)
-DEV uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    uint64_t d = 0;
+DEV uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type = 0) {
+    uint64_t d = (uint64_t)layout_type << 61;
     d |= (uint64_t)((saddr >> 4) & 0x3FFF);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
@@ -76,13 +76,22 @@ struct Cfg {
     int M, N, K;      // M = 128, N multiple of 8 (<= 256), K multiple of the per-instruction K
     int pad;          // extra bytes added to the 8-row / MN-group stride (SBO) -- to test padded, bank-conflict-free strides
     int split;        // 1: 3xTF32 (A = Ah + Al, B = Bh + Bl; D = Ah Bh + Al Bh + Ah Bl)
+    int sw128;        // 1: both operands K-major with the 128-byte swizzle (rows of 128 B, 8-row groups of 1024 B, 16-byte chunk
+                      //    index XOR row % 8; descriptor layout_type 2, SBO 1024); K * element size must be 128
+    int lbo_pad;      // extra bytes on the K-chunk stride (LBO) of the no-swizzle K-major layout
 };
 
 // byte offset of element (mn, k) inside an operand tile (element size es, kk = K extent of the whole tile, nn = MN extent)
-__host__ __device__ inline uint32_t tile_off(int mn_major, int es, int mn, int k, int nn, int kk, int pad, uint32_t *lbo, uint32_t *sbo) {
+__host__ __device__ inline uint32_t tile_off(int mn_major, int es, int mn, int k, int nn, int kk, int pad, uint32_t *lbo, uint32_t *sbo,
+                                             int sw128 = 0, int lbo_pad = 0) {
     const int T = 16 / es;                       // elements per 16 bytes
+    if (sw128) {
+        if (lbo) { *lbo = 16; *sbo = 1024; }
+        const int chunk = (k * es) / 16;
+        return (mn / 8) * 1024 + (mn % 8) * 128 + ((chunk ^ (mn % 8)) * 16) + (k * es) % 16;
+    }
     if (!mn_major) {                             // K-major: core = 8 rows x 16 B; chunks of a row group are LBO apart, row groups SBO apart
-        const uint32_t SBO = 128 + pad, LBO = (nn / 8) * SBO;
+        const uint32_t SBO = 128 + pad, LBO = (nn / 8) * SBO + lbo_pad;
         if (lbo) { *lbo = LBO; *sbo = SBO; }
         return (mn % 8) * 16 + (mn / 8) * SBO + (k / T) * LBO + (k % T) * es;
     }
@@ -93,21 +102,21 @@ __host__ __device__ inline uint32_t tile_off(int mn_major, int es, int mn, int k
 }
 
 __global__ void __launch_bounds__(128, 1) probe_kernel(Cfg c, const float *A, const float *B, float *D) {
-    extern __shared__ __align__(128) unsigned char smem[];
+    extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5;
     const int es = c.fmt == FMT_TF32 ? 4 : 2;
     const int kper = 32 / es;                               // K per instruction: 8 (tf32) / 16 (bf16)
     uint32_t lboA, sboA, lboB, sboB;
-    tile_off(c.a_mn, es, 0, 0, c.M, c.K, c.pad, &lboA, &sboA);
-    tile_off(c.b_mn, es, 0, 0, c.N, c.K, c.pad, &lboB, &sboB);
-    const uint32_t szA = tile_off(c.a_mn, es, c.M - 1, c.K - 1, c.M, c.K, c.pad, nullptr, nullptr) + es;
-    const uint32_t szB = tile_off(c.b_mn, es, c.N - 1, c.K - 1, c.N, c.K, c.pad, nullptr, nullptr) + es;
-    const uint32_t offAh = 0, offAl = (szA + 127) & ~127u, offBh = 2 * offAl, offBl = offBh + ((szB + 127) & ~127u);
+    tile_off(c.a_mn, es, 0, 0, c.M, c.K, c.pad, &lboA, &sboA, c.sw128, c.lbo_pad);
+    tile_off(c.b_mn, es, 0, 0, c.N, c.K, c.pad, &lboB, &sboB, c.sw128, c.lbo_pad);
+    const uint32_t szA = c.sw128 ? (c.M / 8) * 1024 : tile_off(c.a_mn, es, c.M - 1, c.K - 1, c.M, c.K, c.pad, nullptr, nullptr, 0, c.lbo_pad) + es;
+    const uint32_t szB = c.sw128 ? (c.N / 8) * 1024 : tile_off(c.b_mn, es, c.N - 1, c.K - 1, c.N, c.K, c.pad, nullptr, nullptr, 0, c.lbo_pad) + es;
+    const uint32_t offAh = 0, offAl = (szA + 1023) & ~1023u, offBh = 2 * offAl, offBl = offBh + ((szB + 1023) & ~1023u);
 
     auto put = [&](uint32_t base, int mn_major, int mn, int k, int nn, float v, bool lo) {
-        const uint32_t o = base + tile_off(mn_major, es, mn, k, nn, c.K, c.pad, nullptr, nullptr);
+        const uint32_t o = base + tile_off(mn_major, es, mn, k, nn, c.K, c.pad, nullptr, nullptr, c.sw128, c.lbo_pad);
         if (es == 4) {
             float w = v;
             if (lo) w = v - __uint_as_float(__float_as_uint(v) & 0xffffe000u);
@@ -139,14 +148,14 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(Cfg c, const float *A, co
         const uint32_t idesc = make_idesc(c.fmt, c.a_mn, c.b_mn, c.M, c.N);
         const uint32_t sbase = smem_u32(smem);
         // bytes to advance the start address per instruction along K
-        const uint32_t advA = c.a_mn ? (kper / 8) * lboA : (kper * es / 16) * lboA;
-        const uint32_t advB = c.b_mn ? (kper / 8) * lboB : (kper * es / 16) * lboB;
+        const uint32_t advA = c.sw128 ? 32 : c.a_mn ? (kper / 8) * lboA : (kper * es / 16) * lboA;
+        const uint32_t advB = c.sw128 ? 32 : c.b_mn ? (kper / 8) * lboB : (kper * es / 16) * lboB;
         uint32_t acc = 0;
         for (int pass = 0; pass < (c.split ? 3 : 1); ++pass) {
             const uint32_t oa = pass == 1 ? offAl : offAh, ob = pass == 2 ? offBl : offBh;
             for (int k = 0; k < c.K / kper; ++k) {
-                const uint64_t da = make_desc(sbase + oa + k * advA, lboA, sboA);
-                const uint64_t db = make_desc(sbase + ob + k * advB, lboB, sboB);
+                const uint64_t da = make_desc(sbase + oa + k * advA, lboA, sboA, c.sw128 ? 2 : 0);
+                const uint64_t db = make_desc(sbase + ob + k * advB, lboB, sboB, c.sw128 ? 2 : 0);
                 if (c.fmt == FMT_TF32) mma_tf32(tmem, da, db, idesc, acc); else mma_f16(tmem, da, db, idesc, acc);
                 acc = 1;
             }
@@ -234,5 +243,15 @@ int main() {
     bad += run("bf16  A MN-major  B K-major  128x64x64", {FMT_BF16, 1, 0, 128, 64, 64, 0, 0});
     bad += run("bf16  A K-major   B MN-major 128x64x64", {FMT_BF16, 0, 1, 128, 64, 64, 0, 0});
     bad += run("bf16  A K-major   B MN-major 128x32x32", {FMT_BF16, 0, 1, 128, 32, 32, 0, 0});
+    // padded strides of the no-swizzle K-major layout (bank-conflict-free producer stores) and the 128-byte swizzle
+    bad += run("tf32  K/K  SBO 160 LBO +16    128x64x32", {FMT_TF32, 0, 0, 128, 64, 32, 32, 0, 0, 16});
+    bad += run("tf32  K/K  SBO 144            128x64x32", {FMT_TF32, 0, 0, 128, 64, 32, 16, 0, 0, 0});
+    bad += run("tf32  3xTF32 K/K SBO 160 LBO+16 128x64x64", {FMT_TF32, 0, 0, 128, 64, 64, 32, 1, 0, 16});
+    bad += run("tf32  K/K  SWIZZLE_128B       128x64x32", {FMT_TF32, 0, 0, 128, 64, 32, 0, 0, 1, 0});
+    bad += run("tf32  K/K  SWIZZLE_128B       128x256x32", {FMT_TF32, 0, 0, 128, 256, 32, 0, 0, 1, 0});
+    bad += run("tf32  3xTF32 K/K SWIZZLE_128B 128x64x32", {FMT_TF32, 0, 0, 128, 64, 32, 0, 1, 1, 0});
+    bad += run("bf16  K/K  SWIZZLE_128B       128x64x64", {FMT_BF16, 0, 0, 128, 64, 64, 0, 0, 1, 0});
+    bad += run("tf32  K/K  N=16               128x16x32", {FMT_TF32, 0, 0, 128, 16, 32, 0, 0, 0, 0});
+    bad += run("tf32  K/K  N=32 3xTF32        128x32x32", {FMT_TF32, 0, 0, 128, 32, 32, 0, 1, 0, 0});
     return bad;
 }
