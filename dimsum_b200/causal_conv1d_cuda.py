@@ -86,10 +86,11 @@ def conv_xproj_supported(x, weight, x_proj_weight, out=None):
                                 and out.stride(0) % vec == 0 and out.stride(1) % vec == 0 and out.data_ptr() % 16 == 0):
         return False
     n_out, dim = x_proj_weight.shape
-    return (dim == x.shape[1] and dim % kc == 0 and x.shape[2] % vec == 0 and 8 <= n_out <= 256 and n_out % 8 == 0
+    return (dim == x.shape[1] and dim % kc == 0 and x.shape[2] % vec == 0 and 8 <= n_out <= 128 and n_out % 8 == 0
             and x_proj_weight.stride(1) == 1 and x_proj_weight.stride(0) % vec == 0 and x_proj_weight.data_ptr() % 16 == 0
-            and x.stride(0) % vec == 0 and x.stride(1) % vec == 0 and x.data_ptr() % 16 == 0 and 2 <= weight.shape[1] <= 4
-            and x.shape[0] <= 65535)
+            and x.stride(0) % vec == 0 and x.stride(1) % vec == 0 and x.data_ptr() % 16 == 0
+            and weight.dtype == torch.float32 and weight.dim() == 2 and weight.shape[1] == 4 and weight.is_contiguous()
+            and weight.data_ptr() % 16 == 0 and 0 < x.shape[0] <= 65535)
 
 
 def conv_xproj_fwd(x, weight, bias_, x_proj_weight, precise=False, out=None, split=None):
@@ -103,6 +104,11 @@ def conv_xproj_fwd(x, weight, bias_, x_proj_weight, precise=False, out=None, spl
     3xTF32 split for fp32 I/O (fp32-grade results, used when TF32 matmuls are disabled)."""
     batch, dim, seqlen, width = _checks(x, weight, bias_)
     _check(conv_xproj_supported(x, weight, x_proj_weight), "conv_xproj_fwd: unsupported shape or layout (see conv_xproj_supported)")
+    if bias_ is None:
+        bias_ = torch.zeros(dim, device=x.device, dtype=weight.dtype)
+    precise = bool(precise) and x.dtype == torch.float32
+    # low part of the 3xTF32 split of the weight: w - (w with the 13 low mantissa bits cleared), exact in fp32
+    xw_lo = (x_proj_weight - (x_proj_weight.view(torch.int32) & -8192).view(torch.float32)) if precise else None
     vec = 16 // x.element_size()
     if out is not None:
         _check(out.dtype == x.dtype and out.is_cuda and out.shape == x.shape and out.stride(2) == 1
@@ -115,7 +121,8 @@ def conv_xproj_fwd(x, weight, bias_, x_proj_weight, precise=False, out=None, spl
         u = out if out is not None else torch.empty(x.shape, device=x.device, dtype=x.dtype)
         p = _lib.ConvXprojParams()
         p.batch, p.dim, p.seqlen, p.width, p.n_out = batch, dim, seqlen, width, n_out
-        p.io_dtype, p.w_dtype, p.precision = _DT[x.dtype], _DT[weight.dtype], int(bool(precise) and x.dtype == torch.float32)
+        p.io_dtype, p.w_dtype, p.precision = _DT[x.dtype], _DT[weight.dtype], int(precise)
+        p.x_proj_weight_lo = xw_lo.data_ptr() if precise else None
         p.x_batch_stride, p.x_d_stride = x.stride(0), x.stride(1)
         p.u_batch_stride, p.u_d_stride = u.stride(0), u.stride(1)
         if split is None:
@@ -133,7 +140,7 @@ def conv_xproj_fwd(x, weight, bias_, x_proj_weight, precise=False, out=None, spl
             result = (u, dt, bc)
         p.w_d_stride, p.w_width_stride, p.xw_row_stride = weight.stride(0), weight.stride(1), x_proj_weight.stride(0)
         p.x, p.conv_weight, p.x_proj_weight = x.data_ptr(), weight.data_ptr(), x_proj_weight.data_ptr()
-        p.conv_bias = bias_.data_ptr() if bias_ is not None else None
+        p.conv_bias = bias_.data_ptr()
         p.u = u.data_ptr()
         _lib.call("dimsum_conv_xproj_fwd", p, _stream(x))
     return result

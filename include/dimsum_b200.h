@@ -156,8 +156,10 @@ int dimsum_causal_conv1d_bwd(const dimsum_conv_bwd_params *p, void *stream);
  *     x_dbl      = F.linear(rearrange(conv1d_out, "b d l -> (b l) d"), x_proj_weight)
  *     B, C       = rearrange(x_dbl[:, ...], "(b l) dstate -> b 1 dstate l").contiguous()
  * x            : (batch, dim, seqlen) io_dtype, sequence stride 1 (the first half of xz)
- * conv_weight  : (dim, width) w_dtype, conv_bias (dim) w_dtype or NULL; width 2..4; SiLU always applied
- * x_proj_weight: (n_out, dim) io_dtype, row stride xw_row_stride, n_out = dt_rank + 2*dstate (multiple of 8, <= 256)
+ * conv_weight  : (dim, 4) contiguous fp32, conv_bias (dim) fp32 (the model's conv; anything else is DIMSUM_ERR_UNSUPPORTED);
+ *                SiLU always applied
+ * x_proj_weight: (n_out, dim) io_dtype, row stride xw_row_stride, n_out = dt_rank + 2*dstate (multiple of 8, <= 128)
+ * x_proj_weight_lo : precision 1 only: x_proj_weight - tf32_truncate(x_proj_weight), same shape and strides (fp32)
  * u            : (batch, dim, seqlen) io_dtype  = silu(conv(x)), bit-identical to dimsum_causal_conv1d_fwd
  * x_dbl        : x_proj(u), CHANNEL-major, io_dtype: output row e (< n_out) of batch b, token l is written to
  *                x_dbl + b * x_dbl_batch_stride + e * x_dbl_row_stride + l for e < split_rows (or all e when x_dbl_tail is
@@ -169,7 +171,8 @@ int dimsum_causal_conv1d_bwd(const dimsum_conv_bwd_params *p, void *stream);
  * precision    : 0 = one tensor-core pass (TF32 for fp32 I/O -- what cuBLAS does under allow_tf32 -- bf16 / fp16 operands for
  *                16-bit I/O, fp32 accumulation); 1 = 3xTF32 split for fp32 I/O (fp32-grade, ~1e-6 relative)
  * Requires dim % (128 / element size) == 0, seqlen % (16 / element size) == 0 and 16-byte aligned rows; anything else
- * returns DIMSUM_ERR_UNSUPPORTED and the caller runs the two separate steps.
+ * returns DIMSUM_ERR_UNSUPPORTED and the caller runs the two separate steps.  x and x_proj_weight are read through TMA
+ * tensor maps built per call (cuTensorMapEncodeTiled via cudaGetDriverEntryPoint: no link-time libcuda dependency).
  */
 typedef struct {
     int64_t batch, dim, seqlen, width, n_out, split_rows;
@@ -179,7 +182,7 @@ typedef struct {
     int64_t x_dbl_batch_stride, x_dbl_row_stride;
     int64_t tail_batch_stride, tail_row_stride;
     int64_t w_d_stride, w_width_stride, xw_row_stride;
-    const void *x, *conv_weight, *conv_bias, *x_proj_weight;
+    const void *x, *conv_weight, *conv_bias, *x_proj_weight, *x_proj_weight_lo;
     void *u, *x_dbl, *x_dbl_tail;
 } dimsum_conv_xproj_params;
 
