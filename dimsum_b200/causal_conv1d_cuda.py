@@ -76,8 +76,10 @@ def causal_conv1d_fwd_cond(x, weight, bias_, silu_activation, init_x):
     return _fwd_into(x, weight, bias_, silu_activation, init_x)
 
 
-def conv_xproj_supported(x, weight, x_proj_weight, out=None):
+def conv_xproj_supported(x, weight, x_proj_weight, out=None, precise=False):
     """Shapes / layouts the fused conv + x_proj kernel takes (anything else runs the two separate steps)."""
+    if precise and x.dtype == torch.float32 and x_proj_weight.shape[0] > 64:
+        return False                                  # hi + lo weight tiles of more than 64 rows do not fit the shared-memory ring
     if x.dtype not in _DT or x_proj_weight.dtype != x.dtype or not x.is_cuda or x.dim() != 3 or x.stride(2) != 1:
         return False
     es = x.element_size()
@@ -103,7 +105,8 @@ def conv_xproj_fwd(x, weight, bias_, x_proj_weight, precise=False, out=None, spl
     `out` (the reference's `init_states` buffer, causal_conv1d.cpp:326) receives u when given.  `precise` selects the
     3xTF32 split for fp32 I/O (fp32-grade results, used when TF32 matmuls are disabled)."""
     batch, dim, seqlen, width = _checks(x, weight, bias_)
-    _check(conv_xproj_supported(x, weight, x_proj_weight), "conv_xproj_fwd: unsupported shape or layout (see conv_xproj_supported)")
+    _check(conv_xproj_supported(x, weight, x_proj_weight, precise=precise),
+           "conv_xproj_fwd: unsupported shape or layout (see conv_xproj_supported)")
     if bias_ is None:
         bias_ = torch.zeros(dim, device=x.device, dtype=weight.dtype)
     precise = bool(precise) and x.dtype == torch.float32

@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_xproj_kernel(const ConvXproj
     static_assert(!kPrecise || kTf32, "the 3xTF32 split is for fp32 operands");
 
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    __shared__ uint64_t bar_full[kNS], bar_empty[kNS], bar_afree[2];
+    __shared__ uint64_t bar_full[kNS], bar_empty[kNS], bar_afree[kGroups];
     __shared__ uint32_t tmem_slot;
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int w_bytes = S::w_bytes(a.n_out);
@@ -127,14 +127,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_xproj_kernel(const ConvXproj
     const int L = a.seqlen;
     const int n_chunks = a.dim / KC;
     const uint32_t acc_cols = (uint32_t)a.n_out;                         // columns per group accumulator
-    const uint32_t tmem_cols = 2 * a.n_out <= 32 ? 32u : 2 * a.n_out <= 64 ? 64u : 2 * a.n_out <= 128 ? 128u : 256u;
+    const uint32_t need_cols = kGroups * acc_cols;
+    const uint32_t tmem_cols = need_cols <= 32 ? 32u : need_cols <= 64 ? 64u : need_cols <= 128 ? 128u : need_cols <= 256 ? 256u : 512u;
 
     if (warp == 0) umma::tmem_alloc(&tmem_slot, tmem_cols);
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < kNS; ++s) { umma::mbar_init(&bar_full[s], 1); umma::mbar_init(&bar_empty[s], 1); }
-        umma::mbar_init(&bar_afree[0], 1);
-        umma::mbar_init(&bar_afree[1], 1);
+#pragma unroll
+        for (int g = 0; g < kGroups; ++g) umma::mbar_init(&bar_afree[g], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     umma::fence_before_sync();
@@ -244,25 +245,33 @@ __global__ void __launch_bounds__(kThreads, 1) conv_xproj_kernel(const ConvXproj
         }
         // ---- epilogue (group 0): both groups' MMAs done -> sum of the two accumulator rows (thread = token) -> coalesced rows
         if (grp == 0) {
-            const int n0 = (n_chunks + 1) / 2, n1 = n_chunks / 2;        // chunks issued by group 0 / group 1
-            umma::mbar_wait(&bar_afree[0], (n0 - 1) & 1);
-            if (n1 > 0) umma::mbar_wait(&bar_afree[1], (n1 - 1) & 1);
+            int ng[kGroups];                                             // chunks issued by each group
+#pragma unroll
+            for (int g = 0; g < kGroups; ++g) {
+                ng[g] = (n_chunks - g + kGroups - 1) / kGroups;
+                if (ng[g] > 0) umma::mbar_wait(&bar_afree[g], (ng[g] - 1) & 1);
+            }
             umma::fence_after_sync();
             T *ob = reinterpret_cast<T *>(a.xdbl) + (int64_t)b * a.o_bs;
             T *tb = a.tail != nullptr ? reinterpret_cast<T *>(a.tail) + (int64_t)b * a.t_bs : nullptr;
             const int tok = l0 + tid;
             for (int e0 = 0; e0 < a.n_out; e0 += 8) {
-                uint32_t v[8], v1[8];
-                umma::tmem_ld8(tmem + ((uint32_t)(warp * 32) << 16) + e0, v);
-                if (n1 > 0) umma::tmem_ld8(tmem + ((uint32_t)(warp * 32) << 16) + acc_cols + e0, v1);
+                uint32_t v[kGroups][8];
+#pragma unroll
+                for (int g = 0; g < kGroups; ++g)
+                    if (ng[g] > 0) umma::tmem_ld8(tmem + ((uint32_t)(warp * 32) << 16) + g * acc_cols + e0, v[g]);
                 umma::tmem_ld_wait();
                 if (tok < L) {
                     const bool in_tail = tb != nullptr && e0 >= a.split;
                     T *dst = in_tail ? tb + (int64_t)(e0 - a.split) * a.t_rs : ob + (int64_t)e0 * a.o_rs;
                     const int64_t rs = in_tail ? a.t_rs : a.o_rs;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        Io<T>::st(dst + j * rs + tok, __uint_as_float(v[j]) + (n1 > 0 ? __uint_as_float(v1[j]) : 0.f));
+                    for (int j = 0; j < 8; ++j) {
+                        float sum = __uint_as_float(v[0][j]);
+#pragma unroll
+                        for (int g = 1; g < kGroups; ++g) sum += ng[g] > 0 ? __uint_as_float(v[g][j]) : 0.f;
+                        Io<T>::st(dst + j * rs + tok, sum);
+                    }
                 }
             }
         }
@@ -296,7 +305,7 @@ CUtensorMapDataType tm_dtype(int io_dtype) {
 template <typename T, bool kPrecise, int kNS>
 int launch(const ConvXprojArgs &a, int batch, const CUtensorMap &mx, const CUtensorMap &mw, const CUtensorMap &mwl, cudaStream_t stream) {
     auto kern = conv_xproj_kernel<T, kPrecise, kNS>;
-    const int smem = kNS * Slot<T, kPrecise>::bytes(a.n_out) + 2 * (kPrecise ? 2 : 1) * kABytes + 1024;
+    const int smem = kNS * Slot<T, kPrecise>::bytes(a.n_out) + kGroups * (kPrecise ? 2 : 1) * kABytes + 1024;
     if (smem > 227 * 1024) return fail(DIMSUM_ERR_UNSUPPORTED, "conv_xproj_fwd: n_out = %d needs %d bytes of shared memory", a.n_out, smem);
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     dim3 grid((a.seqlen + kTok - 1) / kTok, batch);
@@ -325,7 +334,7 @@ extern "C" int dimsum_conv_xproj_fwd(const dimsum_conv_xproj_params *p, void *st
     DIMSUM_REQUIRE(p->batch <= 65535, DIMSUM_ERR_UNSUPPORTED, "conv_xproj_fwd: batch > 65535");
     const int es = p->io_dtype == DIMSUM_F32 ? 4 : 2;
     const int vec = 16 / es, kc = 128 / es;
-    DIMSUM_REQUIRE(p->n_out >= 8 && p->n_out <= 128 && p->n_out % 8 == 0, DIMSUM_ERR_UNSUPPORTED,
+    DIMSUM_REQUIRE(p->n_out >= 8 && p->n_out <= 128 && p->n_out % 8 == 0 && kGroups * p->n_out <= 512, DIMSUM_ERR_UNSUPPORTED,
                    "conv_xproj_fwd: x_proj rows (dt_rank + 2 dstate = %lld) must be a multiple of 8, at most 128", (long long)p->n_out);
     DIMSUM_REQUIRE(p->dim % kc == 0, DIMSUM_ERR_UNSUPPORTED, "conv_xproj_fwd: dim must be a multiple of %d", kc);
     DIMSUM_REQUIRE(p->seqlen % vec == 0, DIMSUM_ERR_UNSUPPORTED, "conv_xproj_fwd: seqlen must be a multiple of %d", vec);

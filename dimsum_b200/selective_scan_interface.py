@@ -118,12 +118,12 @@ class MambaInnerFn(torch.autograd.Function):
         x, z = xz.chunk(2, dim=1)
         conv1d_bias = conv1d_bias.contiguous() if conv1d_bias is not None else None
         R, Dm = x.shape[0], x.shape[1]
+        precise = x.dtype == torch.float32 and not torch.backends.cuda.matmul.allow_tf32
         if (fused_xproj_enabled() and B_proj_bias is None and C_proj_bias is None and rank % 8 == 0
-                and causal_conv1d_cuda.conv_xproj_supported(x, conv_w, x_proj_weight, out=init_states)):
+                and causal_conv1d_cuda.conv_xproj_supported(x, conv_w, x_proj_weight, out=init_states, precise=precise)):
             # conv + SiLU fused in front of the x_proj contraction (tcgen05): one pass over x writes u once and emits dt
             # as the (rank, R*L) operand of the dt_proj GEMM and B / C in the scan's layout -- no second read of u, no
             # rearrange copies (selective_scan_interface.py:836-866 in one kernel)
-            precise = x.dtype == torch.float32 and not torch.backends.cuda.matmul.allow_tf32
             conv_out, dt2d, bc = causal_conv1d_cuda.conv_xproj_fwd(x, conv_w, conv1d_bias, x_proj_weight, precise,
                                                                    out=init_states, split=rank)
             Bm, Cm = bc[:, :N].unsqueeze(1), bc[:, N:].unsqueeze(1)

@@ -32,6 +32,9 @@ def test_conv_xproj_matches_conv_then_linear(shape, mode):
         pytest.skip("16-bit I/O needs dim % 64 == 0 and seqlen % 8 == 0")
     xz, w, b, xw = _case(R, D, L, E, dtype, seed=D + L)
     x_d = xz.cuda()[:, :D]                                     # first half of xz: batch stride 2*D*L
+    if mode == "fp32-3xtf32" and E > 64:
+        assert not ccc.conv_xproj_supported(x_d, w.cuda(), xw.cuda(), precise=True)
+        pytest.skip("hi + lo weight tiles of more than 64 rows do not fit the ring")
     assert ccc.conv_xproj_supported(x_d, w.cuda(), xw.cuda())
     u, xd = ccc.conv_xproj_fwd(x_d, w.cuda(), b.cuda(), xw.cuda(), precise=(mode == "fp32-3xtf32"))
     u_ref = ccc.causal_conv1d_fwd(x_d, w.cuda(), b.cuda(), True)
