@@ -168,6 +168,133 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def train_cpu_sample(depth=1, latents=1):
+    """Bounded CPU sample of the training step: forward + backward of `latents` latents through the oracle port of the
+    reference CPU path, truncated to `depth` of the 16 blocks (the full step takes minutes on the host); returns seconds."""
+    from oracle import ref_model
+    model = build_model("cpu")
+    sd = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in model.state_dict().items()}
+    z, y = make_inputs(latents)
+    t = torch.full((latents,), 0.5)
+    t0 = time.perf_counter()
+    out = ref_model.dim_forward_oracle(sd, z, t, y, depth=depth, attn_every=0)
+    out.square().mean().backward()
+    return time.perf_counter() - t0
+
+
+def run_train(args, rank, local_rank, world):
+    """--workload train: BASELINE configs[4], DiMSUM-L/2 bf16 training step, DDP over NCCL, one CUDA graph per step."""
+    import torch.distributed as dist
+    from dimsum_b200 import _lib
+    from tools.train_step import TrainStep, init_dist
+    rank, local_rank, world, dev = init_dist()
+    torch.backends.cuda.matmul.allow_tf32 = True
+    B = args.train_batch
+    ts = TrainStep(dev, rank, world, B, "bf16" if args.dtype != "fp32" else "fp32", use_graph=not args.no_graph)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    launches_per_step = None
+    with ClockSampler(local_rank) as clocks:
+        for _ in range(args.warmup):
+            ts.step()
+        barrier()
+        l0 = _lib.launch_count()
+        clocks.mark_start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            loss = ts.step()
+        e1.record()
+        barrier()
+        clocks.mark_end()
+    ms = e0.elapsed_time(e1) / args.steps
+    assert torch.isfinite(loss).all()
+    # end to end: the step's latents and labels come from pinned host memory, the loss goes back to the host
+    x1_h = torch.randn(B, 4, RES, RES).pin_memory()
+    y_h = torch.randint(0, 1000, (B,)).pin_memory()
+    loss_h = torch.empty((), dtype=torch.float32).pin_memory()
+    _, x0_d, _, t_d = ts.draw()
+    for _ in range(2):
+        ts.step((x1_h.to(dev, non_blocking=True), x0_d, y_h.to(dev, non_blocking=True), t_d))
+    barrier()
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record()
+    for _ in range(args.steps):
+        lv = ts.step((x1_h.to(dev, non_blocking=True), x0_d, y_h.to(dev, non_blocking=True), t_d))
+        loss_h.copy_(lv.detach(), non_blocking=True)
+    a1.record()
+    barrier()
+    ms_e2e = a0.elapsed_time(a1) / args.steps
+    # the dominant kernel of this repo in the training step is the scan backward: time its launches in one eager step
+    bwd_events, fwd_events = [], []
+    real_call = _lib.call
+
+    def timed_call(name, params, stream):
+        if name not in ("dimsum_selective_scan_bwd", "dimsum_selective_scan_fwd"):
+            return real_call(name, params, stream)
+        s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s_.record()
+        real_call(name, params, stream)
+        e_.record()
+        (bwd_events if name.endswith("bwd") else fwd_events).append((s_, e_))
+
+    _lib.call = timed_call
+    before = _lib.launch_count()
+    ts.train_on(*ts.draw())
+    torch.cuda.synchronize()
+    launches_per_step = _lib.launch_count() - before
+    _lib.call = real_call
+    bwd_ms = sum(s_.elapsed_time(e_) for s_, e_ in bwd_events) / max(1, len(bwd_events))
+    fwd_ms = sum(s_.elapsed_time(e_) for s_, e_ in fwd_events) / max(1, len(fwd_events))
+    peak_mem = torch.cuda.max_memory_allocated() / 2 ** 30
+    if world > 1:
+        tt = torch.tensor([ms, ms_e2e, bwd_ms, fwd_ms, peak_mem], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms, ms_e2e, bwd_ms, fwd_ms, peak_mem = tt.tolist()
+    if rank == 0:
+        s_b = 2 if args.dtype != "fp32" else 4
+        peak, how = measured_peak()
+        L, D, N = SEQ, D_INNER, D_STATE
+        by_b = s_b * (9 * B * D * L + 2 * B * N * L) + 4 * 2 * B * N * L + 4 * B * D * ((L + 31) // 32) * 2 * N
+        line = {
+            "metric": "DiMSUM-L/2 train latents/s", "value": B * world / (ms * 1e-3), "unit": "latents/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16" if args.dtype != "fp32" else "f32", "data": "synthetic",
+            "config": {"workload": "DiMSUM-L/2 bf16 training step on synthetic latents (BASELINE configs[4]): %d latents per GPU, GVP "
+                                   "velocity loss, DDP gradient all-reduce over NCCL, clip 1.0, fused AdamW lr 1e-4" % B,
+                       "per_gpu_batch": B, "tokens": SEQ, "d_inner": D_INNER, "d_state": D_STATE,
+                       "launch": "eager" if ts.graph is None else "one CUDA graph per step (forward, backward with DDP's bucketed NCCL "
+                                 "all-reduces, clip, AdamW)",
+                       "l2": "activations of one step >> 126 MB L2", "params": sum(p.numel() for p in ts.model.parameters()),
+                       "peak_mem_gb": peak_mem},
+            "e2e": {"value": B * world / (ms_e2e * 1e-3), "unit": "latents/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": (x1_h.numel() * 4 + y_h.numel() * 8) * world, "d2h_bytes_per_step": 4 * world},
+            "gpu_launches": launches_per_step * args.steps * world,
+            "roofline": {"kernel": "scan_bwd_kernel (selective scan backward)", "bound": "hbm",
+                         "achieved": by_b / (bwd_ms * 1e-3) / 1e9, "peak": peak,
+                         "peak_source": how + " (MEASURED_PEAKS.json hbm_gbs, burst copy)", "unit": "GB/s",
+                         "frac": by_b / (bwd_ms * 1e-3) / 1e9 / peak, "traffic": None, "algorithmic_bytes_per_launch": by_b,
+                         "avg_launch_ms": bwd_ms, "launches_timed": len(bwd_events),
+                         "scan_fwd_train_avg_launch_ms": fwd_ms, "timed_in": "one instrumented eager step after the timed region",
+                         "share_of_step": bwd_ms * len(bwd_events) / ms},
+            "clocks": clocks.summary(),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            torch.set_num_threads(os.cpu_count())
+            sec = train_cpu_sample(depth=1, latents=1)
+            line["cpu_baseline"] = {"value": 1.0 / (sec * 16), "unit": "latents/s", "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": "forward + backward of 1 latent through 1 of the 16 DiM-L/2 blocks of the oracle port "
+                                              "(autograd through selective_scan_ref / causal_conv1d_ref semantics), %.1f s, scaled x16; no "
+                                              "optimizer step" % sec}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_b200(args, rank, local_rank, world):
     import torch.distributed as dist
     from dimsum_b200 import _lib
@@ -426,6 +553,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--workload", default="sample", choices=["sample", "train"],
+                    help="sample: CFG denoising evaluation (BASELINE configs[2], the headline); train: bf16 DDP training step (configs[4])")
+    ap.add_argument("--train-batch", type=int, default=32, help="per-GPU batch of --workload train (SURVEY.md 8d config 5)")
     ap.add_argument("--latents", type=int, default=TOTAL_LATENTS)
     ap.add_argument("--px", type=int, default=256, choices=[256, 512], help="image size: 256 (L=256 tokens) or 512 (L=1024, configs[3])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -446,6 +576,11 @@ def main():
         run_reference(args, rank)
         return
     args.warmup = max(args.warmup, 3)
+    if args.workload == "train":
+        if args.dtype == "fp32" and "--dtype" not in sys.argv:
+            args.dtype = "bf16"                       # configs[4] is a bf16-autocast config
+        run_train(args, rank, local_rank, world)
+        return
     run_b200(args, rank, local_rank, world)
 
 

@@ -2,12 +2,17 @@
 
     python tools/train_step.py --steps 5                         # 1 GPU
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/train_step.py --steps 5
+    python bench.py --workload train [--gpus N]                  # the same step behind the bench contract
 
 Mirrors the reference loop (dimsum/train.py:302-321: DDP wrap :180, AdamW(lr=1e-4, wd=0), clip_grad_norm_(1.0)) and the
 GVP velocity loss (dimsum/transport/path.py:228-247 alpha=sin(pi t/2), sigma=cos(pi t/2); transport.py:137-146
-loss = mean((model(xt, t, y) - ut)^2)).  The scan / conv / wavelet forward AND backward run on this repo's kernels;
+loss = mean((model(xt, t, y) - ut)^2)).  The scan / conv(+x_proj) / wavelet forward AND backward run on this repo's kernels;
 the gradient all-reduce is DDP's bucketed NCCL all-reduce over NVLink, overlapped with backward.
-Prints one JSON line: latents/s, ms per step, and the peak memory.
+
+The whole step -- forward, backward with the bucketed all-reduces, gradient clipping, fused AdamW -- is captured into ONE
+CUDA graph and replayed (the step is ~3000 launches for ~60 ms of device work, so eager execution is host-bound).  With DDP
+the capture follows PyTorch's recipe: NCCL async error handling off, DDP constructed and warmed up for 11 iterations on a
+side stream, then the capture.  `--no-graph` launches eagerly.
 """
 import argparse
 import json
@@ -18,7 +23,8 @@ import sys
 import torch
 import torch.distributed as dist
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
 
 
 def gvp_plan(t, x0, x1):
@@ -26,6 +32,89 @@ def gvp_plan(t, x0, x1):
     s, ds = torch.cos(t * math.pi / 2), -math.pi / 2 * torch.sin(t * math.pi / 2)
     e = lambda v: v.view(-1, 1, 1, 1)
     return e(a) * x1 + e(s) * x0, e(da) * x1 + e(ds) * x0
+
+
+class TrainStep:
+    """One optimizer step of config 5 on this rank's GPU: `step()` draws a synthetic batch on the device and runs (or
+    replays) forward + backward (+ DDP all-reduce) + clip + AdamW; returns the loss tensor."""
+
+    def __init__(self, dev, rank, world, batch=32, dtype="bf16", model_name="DiM-L/2", depth=None, use_graph=True, res=32):
+        from dimsum_b200.models_dim import DiM, DiM_models
+        self.dev, self.rank, self.world, self.batch, self.res = dev, rank, world, batch, res
+        torch.manual_seed(0)
+        kw = dict(img_resolution=res, in_channels=4, num_classes=1000, label_dropout=0.1,
+                  ssm_cfg={"freeze_dead_cond_proj": True})     # DDP(find_unused_parameters=False) must not wait for dcond = None
+        with torch.device(dev):
+            model = DiM_models[model_name](**kw) if depth is None else DiM(depth=depth, hidden_size=1024, **kw)
+        with torch.no_grad():
+            for n, p in model.named_parameters():
+                if "adaLN_modulation" in n or n.startswith("final_layer.linear"):
+                    p.normal_(0, 0.02)
+        self.model = model.to(dev).train()
+        self.amp = torch.autocast("cuda", dtype=torch.bfloat16, enabled=dtype == "bf16")
+        self.g = torch.Generator(device=dev).manual_seed(rank)
+        self.use_graph = use_graph
+        self.graph = None
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            # DDP is constructed on the side stream so that its bucket streams / events are captured consistently
+            self.ddp = (torch.nn.parallel.DistributedDataParallel(self.model, device_ids=[dev.index], gradient_as_bucket_view=True)
+                        if world > 1 else self.model)
+            self.opt = torch.optim.AdamW(self.model.parameters(), lr=1e-4, weight_decay=0, capturable=use_graph, fused=True)
+            if use_graph:
+                self.static = [b.clone() for b in self.draw()]
+                for _ in range(11 if world > 1 else 3):        # DDP needs 11 warm-up iterations before capture
+                    self.train_on(*self.static)
+        torch.cuda.current_stream().wait_stream(side)
+        if use_graph:
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            self.graph = torch.cuda.CUDAGraph()
+            self.opt.zero_grad(set_to_none=True)
+            with torch.cuda.graph(self.graph):
+                self.static_loss = self.train_on(*self.static)
+
+    def draw(self):
+        x1 = torch.randn(self.batch, 4, self.res, self.res, generator=self.g, device=self.dev)
+        y = torch.randint(0, 1000, (self.batch,), generator=self.g, device=self.dev)
+        t = torch.rand(self.batch, generator=self.g, device=self.dev)
+        return x1, torch.randn(x1.shape, generator=self.g, device=self.dev), y, t
+
+    def train_on(self, x1, x0, y, t):
+        xt, ut = gvp_plan(t, x0, x1)
+        with self.amp:
+            out = self.ddp(xt, t, y)
+        loss = (out.float() - ut).square().mean()
+        self.opt.zero_grad(set_to_none=True)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(self.model.parameters(), 1.0)
+        self.opt.step()
+        return loss
+
+    def step(self, batch=None):
+        """`batch`: optional (x1, x0, y, t) device tensors (the end-to-end leg of bench.py copies them from pinned host memory)."""
+        src = batch if batch is not None else self.draw()
+        if self.graph is None:
+            return self.train_on(*src)
+        for dst, s in zip(self.static, src):
+            dst.copy_(s, non_blocking=True)
+        self.graph.replay()
+        return self.static_loss
+
+    def missing_grads(self):
+        return [n for n, p in self.model.named_parameters() if p.requires_grad and p.grad is None and "cond_proj" not in n]
+
+
+def init_dist():
+    rank, local, world = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("LOCAL_RANK", 0), ("WORLD_SIZE", 1)))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")     # required to capture NCCL collectives in a CUDA graph
+        dist.init_process_group("nccl", device_id=dev)
+    return rank, local, world, dev
 
 
 def main():
@@ -36,81 +125,21 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--model", default="DiM-L/2")
     ap.add_argument("--depth", type=int, default=None, help="override depth (smoke runs)")
-    ap.add_argument("--graph", action="store_true",
-                    help="capture forward + backward + clip + AdamW of one step in a CUDA graph and replay it (single GPU): the "
-                         "step is ~3000 launches for 86 ms of device work, so eager execution is host-bound")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying a CUDA graph")
     ap.add_argument("--profile", default=None, help="write a torch.profiler kernel table of one extra step to this file")
     args = ap.parse_args()
-    rank, local, world = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("LOCAL_RANK", 0), ("WORLD_SIZE", 1)))
-    dev = torch.device("cuda", local)
-    torch.cuda.set_device(dev)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    rank, local, world, dev = init_dist()
     torch.backends.cuda.matmul.allow_tf32 = True
-    from dimsum_b200.models_dim import DiM, DiM_models
-    torch.manual_seed(0)
-    kw = dict(img_resolution=32, in_channels=4, num_classes=1000, label_dropout=0.1)
-    with torch.device(dev):
-        model = DiM_models[args.model](**kw) if args.depth is None else DiM(depth=args.depth, hidden_size=1024, **kw)
-    with torch.no_grad():
-        for n, p in model.named_parameters():
-            if "adaLN_modulation" in n or n.startswith("final_layer.linear"):
-                p.normal_(0, 0.02)
-    model = model.to(dev).train()
-    ddp = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local]) if world > 1 else model
-    use_graph = args.graph and world == 1
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0, capturable=use_graph, fused=True)   # same update, one kernel
-    g = torch.Generator(device=dev).manual_seed(rank)
-    amp = torch.autocast("cuda", dtype=torch.bfloat16, enabled=args.dtype == "bf16")
-
-    def draw():
-        x1 = torch.randn(args.batch, 4, 32, 32, generator=g, device=dev)
-        y = torch.randint(0, 1000, (args.batch,), generator=g, device=dev)
-        t = torch.rand(args.batch, generator=g, device=dev)
-        return x1, torch.randn(x1.shape, generator=g, device=dev), y, t
-
-    def train_on(x1, x0, y, t):
-        xt, ut = gvp_plan(t, x0, x1)
-        with amp:
-            out = ddp(xt, t, y)
-        loss = (out.float() - ut).square().mean()
-        opt.zero_grad(set_to_none=True)
-        loss.backward()
-        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
-        opt.step()
-        return loss
-
-    if use_graph:
-        static = [b.clone() for b in draw()]
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):                       # warm-up on a side stream, as graph capture requires
-            for _ in range(3):
-                train_on(*static)
-        torch.cuda.current_stream().wait_stream(side)
-        graph = torch.cuda.CUDAGraph()
-        opt.zero_grad(set_to_none=True)
-        with torch.cuda.graph(graph):
-            static_loss = train_on(*static)
-
-        def step():
-            for dst, src in zip(static, draw()):
-                dst.copy_(src)
-            graph.replay()
-            return static_loss
-    else:
-        def step():
-            return train_on(*draw())
-
+    ts = TrainStep(dev, rank, world, args.batch, args.dtype, args.model, args.depth, use_graph=not args.no_graph)
     for _ in range(args.warmup):
-        step()
+        ts.step()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        loss = step()
+        loss = ts.step()
     e1.record()
     torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
@@ -119,16 +148,16 @@ def main():
     if args.profile and rank == 0:
         from torch.profiler import ProfilerActivity, profile
         with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
-            step()
+            ts.step()
             torch.cuda.synchronize()
         with open(args.profile, "w") as f:
             f.write(prof.key_averages().table(sort_by="self_cuda_time_total", row_limit=70, max_name_column_width=90))
     if rank == 0:
         print(json.dumps({"metric": "DiMSUM-L/2 train latents/s", "value": args.batch * world / (ms.item() * 1e-3),
                           "ms_per_step": ms.item(), "n_gpus": world, "per_gpu_batch": args.batch, "dtype": args.dtype,
-                          "launch": "CUDA graph replay" if use_graph else "eager",
+                          "launch": "CUDA graph replay" if ts.graph is not None else "eager",
                           "loss": float(loss), "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30,
-                          "missing_grads": [n for n, p in model.named_parameters() if p.grad is None and "cond_proj" not in n]}))
+                          "missing_grads": ts.missing_grads()}))
     if world > 1:
         dist.destroy_process_group()
 
