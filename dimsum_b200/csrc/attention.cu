@@ -1,0 +1,315 @@
+// Softmax attention for the DiMSUM fusion / DiT blocks on TMA + tcgen05 tensor cores (sm_100a), fp32 I/O, TF32 math.
+//
+// Replaces F.scaled_dot_product_attention at the three call sites of the released model
+// (dimsum/attention_fusion.py:61-84 -- two cross attentions per block, 8 heads x 64 -- and the shared DiTBlock,
+// dimsum/models_dim.py:1532-1554, 16 heads x 64) for the sequence lengths of the 256px configuration (256 tokens).  In the
+// fp32 sampling step the library kernel PyTorch picks for fp32 (`fmha_cutlassF_f32_aligned_64x64_rf_sm80`, an Ampere
+// kernel) was 24 % of the device time.
+//
+// One CTA per (batch, head).  K (all <= 256 keys, two 128-byte column blocks of head_dim) and the query tiles arrive by TMA
+// in the tensor core's SWIZZLE_128B K-major layout; V is transposed on the way in (V^T is the K-major B operand of P V;
+// kind::tf32 has no MN-major mode) with conflict-free 4-byte stores.  Per 128-query tile:
+//   S = Q K^T      8 tcgen05.mma (M 128, N = keys, K 8) into TMEM columns [0, keys)
+//   softmax        8 warps: thread = (row, half of the keys); tcgen05.ld, row max / sum exchanged through shared memory,
+//                  p = 2^((s - max) scale log2 e) written back IN PLACE with tcgen05.st (P never touches shared memory)
+//   O = P V        keys / 8 tcgen05.mma with the A operand read from TMEM, into TMEM columns [256, 320)
+//   epilogue       tcgen05.ld, times 1 / row sum, 128-byte contiguous stores straight into the (batch, tokens, heads x 64)
+//                  layout the output projection reads (no transpose / cat copies).
+// The second query tile of a 256-token row reuses K and V^T; its Q tile is prefetched while the first is in flight.
+// TF32 (10-bit mantissa, fp32 accumulate) is what cuBLAS uses for the surrounding GEMMs under allow_tf32; callers that
+// disable TF32 keep the library SDPA.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace dimsum {
+namespace {
+
+constexpr int kHd = 64;            // head dim
+constexpr int kQT = 128;           // queries per tile == MMA M
+constexpr int kMaxKeys = 256;
+constexpr int kAttnThreads = 256;
+constexpr int kOCol = 256;         // TMEM column of the O accumulator (S / P occupy [0, keys))
+
+struct AttnArgs {
+    const float *v;
+    float *out;
+    int64_t v_bs, v_hs, v_ts, o_bs, o_hs, o_ts;
+    int nq, nk, heads;
+    int pos_q[3], pos_k[3];        // position of (token, head, batch) in the stride-sorted outer dims of the tensor maps
+    float scale_log2e;
+};
+
+DEV void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(umma::smem_u32(bar)), "r"(bytes) : "memory");
+}
+DEV void tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(umma::smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(umma::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+                 "r"(c3)
+                 : "memory");
+}
+// tcgen05.mma with the A operand in TMEM (rows = lanes, K along columns), B from a shared-memory descriptor
+DEV void mma_ts_tf32(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n"
+                 ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate));
+}
+DEV void load_tile(void *dst, const CUtensorMap *map, uint64_t *bar, const int (&pos)[3], int d0, int tok, int h, int b) {
+    int c[3];
+    c[pos[0]] = tok; c[pos[1]] = h; c[pos[2]] = b;
+    tma_load_4d(dst, map, bar, d0, c[0], c[1], c[2]);
+}
+
+__global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const AttnArgs a, const __grid_constant__ CUtensorMap map_q,
+                                                                    const __grid_constant__ CUtensorMap map_k) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ uint64_t bar_k, bar_q[2], bar_s, bar_o;
+    __shared__ uint32_t tmem_slot;
+    __shared__ float red_max[2][kQT], red_sum[2][kQT];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int nk = a.nk;
+    const uint32_t k_blk = (uint32_t)nk * 128;                  // bytes of one 128-byte-wide column block of K (nk rows)
+    unsigned char *Ks = smem;                                   // [2 column blocks of head_dim][nk rows][128 B]
+    unsigned char *Vt = Ks + 2 * k_blk;                         // [nk / 32 column blocks of keys][64 rows (head_dim)][128 B]
+    unsigned char *Qs = Vt + (uint32_t)(nk / 32) * 8192;        // [2 buffers][2 column blocks][128 rows][128 B]
+    constexpr uint32_t q_blk = kQT * 128, q_buf = 2 * q_blk;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int h = blockIdx.x, b = blockIdx.y;
+    const int n_qt = (a.nq + kQT - 1) / kQT;
+
+    if (warp == 0) umma::tmem_alloc(&tmem_slot, 512);
+    if (tid == 0) {
+        umma::mbar_init(&bar_k, 1); umma::mbar_init(&bar_q[0], 1); umma::mbar_init(&bar_q[1], 1);
+        umma::mbar_init(&bar_s, 1); umma::mbar_init(&bar_o, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+
+    if (tid == 0) {                                             // K (both column blocks) and the first two query tiles
+        mbar_expect_tx(&bar_k, 2 * k_blk);
+        load_tile(Ks, &map_k, &bar_k, a.pos_k, 0, 0, h, b);
+        load_tile(Ks + k_blk, &map_k, &bar_k, a.pos_k, 32, 0, h, b);
+        for (int t = 0; t < 2 && t < n_qt; ++t) {
+            mbar_expect_tx(&bar_q[t], q_buf);
+            load_tile(Qs + t * q_buf, &map_q, &bar_q[t], a.pos_q, 0, t * kQT, h, b);
+            load_tile(Qs + t * q_buf + q_blk, &map_q, &bar_q[t], a.pos_q, 32, t * kQT, h, b);
+        }
+    }
+    // V^T: lane = key inside a 32-key column block, item = (column block, quad of head_dim); 4-byte stores of a warp fall in
+    // 32 distinct banks (one 128-byte row, swizzled chunk = lane / 4)
+    {
+        const float *vb = a.v + (int64_t)b * a.v_bs + (int64_t)h * a.v_hs;
+        for (int item = warp; item < (nk / 32) * 16; item += kAttnThreads / 32) {
+            const int kb = item >> 4, q = item & 15;
+            const float4 v4 = *reinterpret_cast<const float4 *>(vb + (int64_t)(kb * 32 + lane) * a.v_ts + 4 * q);
+            unsigned char *blk = Vt + kb * 8192;
+            const float vals[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                *reinterpret_cast<float *>(blk + umma::sw128_off(4 * q + i, lane >> 2) + (lane & 3) * 4) = vals[i];
+        }
+    }
+    umma::fence_smem_to_async();
+    __syncthreads();
+
+    const uint32_t idesc_s = umma::idesc(umma::kFmtTF32, kQT, nk);
+    const uint32_t idesc_o = umma::idesc(umma::kFmtTF32, kQT, kHd);
+    const int row = 32 * (warp & 3) + lane, half = warp >> 2;      // this thread's accumulator row and half of the columns
+    const uint32_t lane_base = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
+    const int cols_half = nk / 2;                                   // S columns per half (multiple of 16)
+
+    for (int qt = 0; qt < n_qt; ++qt) {
+        const int buf = qt & 1;
+        if (tid == 0) {
+            if (qt == 0) umma::mbar_wait(&bar_k, 0);
+            umma::mbar_wait(&bar_q[buf], (qt >> 1) & 1);
+            umma::fence_after_sync();
+            const uint32_t sq = umma::smem_u32(Qs + buf * q_buf), sk = umma::smem_u32(Ks);
+#pragma unroll
+            for (int cb = 0; cb < 2; ++cb)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma::mma<true>(tmem, umma::desc_sw128(sq + cb * q_blk + k * 32), umma::desc_sw128(sk + cb * k_blk + k * 32), idesc_s,
+                                    (cb | k) != 0);
+            umma::commit(&bar_s);
+        }
+        umma::mbar_wait(&bar_s, qt & 1);
+        umma::fence_after_sync();
+        if (tid == 0 && qt + 2 < n_qt) {                            // the Q buffer is free again: prefetch the tile after next
+            mbar_expect_tx(&bar_q[buf], q_buf);
+            load_tile(Qs + buf * q_buf, &map_q, &bar_q[buf], a.pos_q, 0, (qt + 2) * kQT, h, b);
+            load_tile(Qs + buf * q_buf + q_blk, &map_q, &bar_q[buf], a.pos_q, 32, (qt + 2) * kQT, h, b);
+        }
+        // ---- softmax over this thread's half of row `row`
+        float m = -INFINITY;
+        for (int c0 = 0; c0 < cols_half; c0 += 16) {
+            uint32_t v[16];
+            umma::tmem_ld16(lane_base + half * cols_half + c0, v);
+            umma::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) m = fmaxf(m, __uint_as_float(v[j]));
+        }
+        red_max[half][row] = m;
+        __syncthreads();
+        m = fmaxf(red_max[0][row], red_max[1][row]) * a.scale_log2e;
+        float sum = 0.f;
+        for (int c0 = 0; c0 < cols_half; c0 += 32) {
+            uint32_t v[32];
+            if (c0 + 32 <= cols_half) {
+                umma::tmem_ld32(lane_base + half * cols_half + c0, v);
+            } else {                                               // cols_half % 32 == 16: last 16 columns
+                uint32_t w[16];
+                umma::tmem_ld16(lane_base + half * cols_half + c0, w);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { v[j] = w[j]; v[16 + j] = __float_as_uint(-INFINITY); }
+            }
+            umma::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float p = ex2_mufu(fmaf(__uint_as_float(v[j]), a.scale_log2e, -m));
+                sum += p;
+                v[j] = __float_as_uint(p);
+            }
+            if (c0 + 32 <= cols_half) {
+                umma::tmem_st32(lane_base + half * cols_half + c0, v);
+            } else {
+                // 16-column tail: store the first 16 values with two 8-column stores is not available here; use st32 on an
+                // aligned window that stays inside [0, nk): the extra 16 columns belong to the other half only when half == 0
+                uint32_t w2[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) w2[j] = v[j];
+                asm volatile(
+                    "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n"
+                    ::"r"(lane_base + half * cols_half + c0), "r"(w2[0]), "r"(w2[1]), "r"(w2[2]), "r"(w2[3]), "r"(w2[4]), "r"(w2[5]),
+                    "r"(w2[6]), "r"(w2[7]), "r"(w2[8]), "r"(w2[9]), "r"(w2[10]), "r"(w2[11]), "r"(w2[12]), "r"(w2[13]), "r"(w2[14]), "r"(w2[15])
+                    : "memory");
+            }
+        }
+        umma::tmem_st_wait();
+        red_sum[half][row] = sum;
+        umma::fence_before_sync();
+        __syncthreads();
+        // ---- O = P V: A from TMEM (P, columns [0, nk)), B = V^T from shared memory
+        if (tid == 0) {
+            umma::fence_after_sync();
+            const uint32_t sv = umma::smem_u32(Vt);
+            for (int kk = 0; kk < nk / 8; ++kk)
+                mma_ts_tf32(tmem + kOCol, tmem + kk * 8, umma::desc_sw128(sv + (kk >> 2) * 8192 + (kk & 3) * 32), idesc_o, kk != 0);
+            umma::commit(&bar_o);
+        }
+        umma::mbar_wait(&bar_o, qt & 1);
+        umma::fence_after_sync();
+        // ---- epilogue: thread = (row, 32 of the 64 output columns)
+        {
+            uint32_t v[32];
+            umma::tmem_ld32(lane_base + kOCol + half * 32, v);
+            umma::tmem_ld_wait();
+            const float inv = 1.f / (red_sum[0][row] + red_sum[1][row]);
+            const int tok = qt * kQT + row;
+            if (tok < a.nq) {
+                float *dst = a.out + (int64_t)b * a.o_bs + (int64_t)h * a.o_hs + (int64_t)tok * a.o_ts + half * 32;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4 *>(dst + j) = make_float4(__uint_as_float(v[j]) * inv, __uint_as_float(v[j + 1]) * inv,
+                                                                       __uint_as_float(v[j + 2]) * inv, __uint_as_float(v[j + 3]) * inv);
+            }
+        }
+        umma::fence_before_sync();
+        __syncthreads();                                            // S / P columns, red_* and O are free for the next tile
+        umma::fence_after_sync();
+    }
+    if (warp == 0) umma::tmem_dealloc(tmem, 512);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// 4-D map over (head_dim, then token / head / batch sorted by stride); box = 32 head_dim values (128 bytes) x `rows` tokens
+int make_map(EncodeTiledFn enc, CUtensorMap *m, const void *ptr, int64_t n_tok, int64_t n_head, int64_t n_batch, int64_t s_tok,
+             int64_t s_head, int64_t s_batch, int rows, int (&pos)[3]) {
+    int64_t size[3] = {n_tok, n_head, n_batch}, stride[3] = {s_tok, s_head, s_batch};
+    int order[3] = {0, 1, 2};
+    for (int i = 0; i < 3; ++i)
+        for (int j = i + 1; j < 3; ++j)
+            if (stride[order[j]] < stride[order[i]]) { const int t = order[i]; order[i] = order[j]; order[j] = t; }
+    cuuint64_t dims[4] = {(cuuint64_t)kHd, 0, 0, 0}, strides[3];
+    cuuint32_t box[4] = {32u, 1u, 1u, 1u}, ones[4] = {1u, 1u, 1u, 1u};
+    for (int i = 0; i < 3; ++i) {
+        dims[1 + i] = (cuuint64_t)size[order[i]];
+        strides[i] = (cuuint64_t)stride[order[i]] * 4;
+        pos[order[i]] = i;
+        if (order[i] == 0) box[1 + i] = (cuuint32_t)rows;
+    }
+    return (int)enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void *>(ptr), dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+}
+
+}  // namespace
+}  // namespace dimsum
+
+using namespace dimsum;
+
+extern "C" int dimsum_attention_fwd(const dimsum_attention_params *p, void *stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    DIMSUM_REQUIRE(p != nullptr, DIMSUM_ERR_INVALID, "attention_fwd: null params");
+    if (p->batch == 0 || p->heads == 0) return DIMSUM_OK;
+    DIMSUM_REQUIRE(p->batch > 0 && p->heads > 0 && p->seqlen_q > 0 && p->seqlen_k > 0, DIMSUM_ERR_INVALID, "attention_fwd: bad sizes");
+    DIMSUM_REQUIRE(p->q && p->k && p->v && p->out, DIMSUM_ERR_INVALID, "attention_fwd: null pointer");
+    DIMSUM_REQUIRE(p->dtype == DIMSUM_F32, DIMSUM_ERR_UNSUPPORTED, "attention_fwd: fp32 I/O only (16-bit inputs keep the library flash kernel)");
+    DIMSUM_REQUIRE(p->head_dim == kHd, DIMSUM_ERR_UNSUPPORTED, "attention_fwd: head_dim must be 64");
+    DIMSUM_REQUIRE(p->seqlen_k <= kMaxKeys && p->seqlen_k % 32 == 0, DIMSUM_ERR_UNSUPPORTED,
+                   "attention_fwd: seqlen_k must be a multiple of 32, at most 256 (longer sequences keep the library kernel)");
+    DIMSUM_REQUIRE(p->batch <= 65535, DIMSUM_ERR_UNSUPPORTED, "attention_fwd: batch > 65535");
+    auto ok = [&](const void *ptr, int64_t s0, int64_t s1, int64_t s2) {
+        return aligned16(ptr) && s0 % 4 == 0 && s1 % 4 == 0 && s2 % 4 == 0 && s0 > 0 && s1 > 0 && s2 > 0;
+    };
+    DIMSUM_REQUIRE(ok(p->q, p->q_batch_stride, p->q_head_stride, p->q_token_stride) &&
+                       ok(p->k, p->k_batch_stride, p->k_head_stride, p->k_token_stride) &&
+                       ok(p->v, p->v_batch_stride, p->v_head_stride, p->v_token_stride) &&
+                       ok(p->out, p->out_batch_stride, p->out_head_stride, p->out_token_stride),
+                   DIMSUM_ERR_UNSUPPORTED, "attention_fwd: q, k, v, out need 16-byte aligned rows and positive strides");
+    EncodeTiledFn enc = encode_tiled();
+    DIMSUM_REQUIRE(enc != nullptr, DIMSUM_ERR_CUDA, "attention_fwd: cuTensorMapEncodeTiled is not available from this driver");
+
+    AttnArgs a;
+    CUtensorMap mq, mk;
+    int r = make_map(enc, &mq, p->q, p->seqlen_q, p->heads, p->batch, p->q_token_stride, p->q_head_stride, p->q_batch_stride, kQT, a.pos_q);
+    DIMSUM_REQUIRE(r == 0, DIMSUM_ERR_CUDA, "attention_fwd: cuTensorMapEncodeTiled(q) failed with %d", r);
+    r = make_map(enc, &mk, p->k, p->seqlen_k, p->heads, p->batch, p->k_token_stride, p->k_head_stride, p->k_batch_stride, (int)p->seqlen_k,
+                 a.pos_k);
+    DIMSUM_REQUIRE(r == 0, DIMSUM_ERR_CUDA, "attention_fwd: cuTensorMapEncodeTiled(k) failed with %d", r);
+    a.v = reinterpret_cast<const float *>(p->v); a.out = reinterpret_cast<float *>(p->out);
+    a.v_bs = p->v_batch_stride; a.v_hs = p->v_head_stride; a.v_ts = p->v_token_stride;
+    a.o_bs = p->out_batch_stride; a.o_hs = p->out_head_stride; a.o_ts = p->out_token_stride;
+    a.nq = (int)p->seqlen_q; a.nk = (int)p->seqlen_k; a.heads = (int)p->heads;
+    a.scale_log2e = p->scale * kLog2e;
+
+    const int smem = 2 * (int)p->seqlen_k * 128 + ((int)p->seqlen_k / 32) * 8192 + 2 * 2 * kQT * 128 + 1024;
+    static std::atomic<unsigned long long> configured{0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!(configured.load(std::memory_order_acquire) >> (dev & 63) & 1ull)) {
+        cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        configured.fetch_or(1ull << (dev & 63), std::memory_order_release);
+    }
+    dim3 grid((unsigned)p->heads, (unsigned)p->batch);
+    attention_kernel<<<grid, kAttnThreads, smem, stream>>>(a, mq, mk);
+    return check_launch("attention_fwd");
+}
