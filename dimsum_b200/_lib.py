@@ -109,6 +109,7 @@ ScanBwdParams = STRUCTS["dimsum_scan_bwd_params"]
 ConvFwdParams = STRUCTS["dimsum_conv_fwd_params"]
 ConvBwdParams = STRUCTS["dimsum_conv_bwd_params"]
 ConvXprojParams = STRUCTS["dimsum_conv_xproj_params"]
+AttentionParams = STRUCTS["dimsum_attention_params"]
 GatherParams = STRUCTS["dimsum_gather_params"]
 WaveletParams = STRUCTS["dimsum_wavelet_params"]
 RowwiseParams = STRUCTS["dimsum_rowwise_params"]
@@ -125,6 +126,7 @@ ENTRY_POINTS = {
     "dimsum_causal_conv1d_fwd": ConvFwdParams,
     "dimsum_causal_conv1d_bwd": ConvBwdParams,
     "dimsum_conv_xproj_fwd": ConvXprojParams,
+    "dimsum_attention_fwd": AttentionParams,
     "dimsum_token_gather": GatherParams,
     "dimsum_wavelet_packet_fwd": WaveletParams,
     "dimsum_wavelet_packet_inv": WaveletParams,

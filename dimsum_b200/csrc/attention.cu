@@ -20,6 +20,8 @@
 // disable TF32 keep the library SDPA.
 #include <cuda.h>
 
+#include <atomic>
+
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -121,7 +123,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const AttnAr
     const uint32_t idesc_o = umma::idesc(umma::kFmtTF32, kQT, kHd);
     const int row = 32 * (warp & 3) + lane, half = warp >> 2;      // this thread's accumulator row and half of the columns
     const uint32_t lane_base = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
-    const int cols_half = nk / 2;                                   // S columns per half (multiple of 16)
+    const int cols_half = nk / 2;                                   // S columns per half (multiple of 32)
 
     for (int qt = 0; qt < n_qt; ++qt) {
         const int buf = qt & 1;
@@ -160,14 +162,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const AttnAr
         float sum = 0.f;
         for (int c0 = 0; c0 < cols_half; c0 += 32) {
             uint32_t v[32];
-            if (c0 + 32 <= cols_half) {
-                umma::tmem_ld32(lane_base + half * cols_half + c0, v);
-            } else {                                               // cols_half % 32 == 16: last 16 columns
-                uint32_t w[16];
-                umma::tmem_ld16(lane_base + half * cols_half + c0, w);
-#pragma unroll
-                for (int j = 0; j < 16; ++j) { v[j] = w[j]; v[16 + j] = __float_as_uint(-INFINITY); }
-            }
+            umma::tmem_ld32(lane_base + half * cols_half + c0, v);
             umma::tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -175,20 +170,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const AttnAr
                 sum += p;
                 v[j] = __float_as_uint(p);
             }
-            if (c0 + 32 <= cols_half) {
-                umma::tmem_st32(lane_base + half * cols_half + c0, v);
-            } else {
-                // 16-column tail: store the first 16 values with two 8-column stores is not available here; use st32 on an
-                // aligned window that stays inside [0, nk): the extra 16 columns belong to the other half only when half == 0
-                uint32_t w2[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) w2[j] = v[j];
-                asm volatile(
-                    "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n"
-                    ::"r"(lane_base + half * cols_half + c0), "r"(w2[0]), "r"(w2[1]), "r"(w2[2]), "r"(w2[3]), "r"(w2[4]), "r"(w2[5]),
-                    "r"(w2[6]), "r"(w2[7]), "r"(w2[8]), "r"(w2[9]), "r"(w2[10]), "r"(w2[11]), "r"(w2[12]), "r"(w2[13]), "r"(w2[14]), "r"(w2[15])
-                    : "memory");
-            }
+            umma::tmem_st32(lane_base + half * cols_half + c0, v);
         }
         umma::tmem_st_wait();
         red_sum[half][row] = sum;
@@ -274,8 +256,8 @@ extern "C" int dimsum_attention_fwd(const dimsum_attention_params *p, void *stre
     DIMSUM_REQUIRE(p->q && p->k && p->v && p->out, DIMSUM_ERR_INVALID, "attention_fwd: null pointer");
     DIMSUM_REQUIRE(p->dtype == DIMSUM_F32, DIMSUM_ERR_UNSUPPORTED, "attention_fwd: fp32 I/O only (16-bit inputs keep the library flash kernel)");
     DIMSUM_REQUIRE(p->head_dim == kHd, DIMSUM_ERR_UNSUPPORTED, "attention_fwd: head_dim must be 64");
-    DIMSUM_REQUIRE(p->seqlen_k <= kMaxKeys && p->seqlen_k % 32 == 0, DIMSUM_ERR_UNSUPPORTED,
-                   "attention_fwd: seqlen_k must be a multiple of 32, at most 256 (longer sequences keep the library kernel)");
+    DIMSUM_REQUIRE(p->seqlen_k <= kMaxKeys && p->seqlen_k % 64 == 0, DIMSUM_ERR_UNSUPPORTED,
+                   "attention_fwd: seqlen_k must be a multiple of 64, at most 256 (longer sequences keep the library kernel)");
     DIMSUM_REQUIRE(p->batch <= 65535, DIMSUM_ERR_UNSUPPORTED, "attention_fwd: batch > 65535");
     auto ok = [&](const void *ptr, int64_t s0, int64_t s1, int64_t s2) {
         return aligned16(ptr) && s0 % 4 == 0 && s1 % 4 == 0 && s2 % 4 == 0 && s0 > 0 && s1 > 0 && s2 > 0;

@@ -26,6 +26,7 @@ import torch.nn.functional as F
 
 from . import fused
 from . import scanning_orders as so
+from .attention import attention, attention_supported
 from .mamba_simple import CondMamba
 from .wavelet import wavelet_packet, wavelet_packet_inverse
 
@@ -174,6 +175,8 @@ class Attention(nn.Module):
     def forward(self, x):
         B, N, C = x.shape
         q, k, v = self.qkv(x).view(B, N, 3, self.num_heads, self.head_dim).permute(2, 0, 3, 1, 4).unbind(0)
+        if attention_supported(q, k, v):          # fp32 sampling with TF32 allowed: the TMA + tcgen05 kernel of this repo
+            return self.proj(attention(q, k, v))  # already (B, N, C): no transpose copy
         return self.proj(F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, N, C))
 
 
@@ -211,6 +214,12 @@ class CrossAttentionFusion(nn.Module):
         B, N, C = x1.shape
         q1, k1, v1 = self.qkv1(x1).view(B, N, 3, self.num_heads, self.head_dim).permute(2, 0, 3, 1, 4).unbind(0)
         q2, k2, v2 = self.qkv2(x2).view(B, N, 3, self.num_heads, self.head_dim).permute(2, 0, 3, 1, 4).unbind(0)
+        if attention_supported(q1, k2, v2) and attention_supported(q2, k1, v1):
+            # both cross attentions write their halves of the (B, N, 2C) input of `proj` directly: no transpose, no cat
+            both = torch.empty((B, N, 2 * C), device=x1.device, dtype=q1.dtype)
+            attention(q1, k2, v2, out=both[:, :, :C].view(B, N, self.num_heads, self.head_dim))
+            attention(q2, k1, v1, out=both[:, :, C:].view(B, N, self.num_heads, self.head_dim))
+            return self.proj(both)
         x12 = F.scaled_dot_product_attention(q1, k2, v2).transpose(1, 2).reshape(B, N, C)
         x21 = F.scaled_dot_product_attention(q2, k1, v1).transpose(1, 2).reshape(B, N, C)
         return self.proj(torch.cat((x12, x21), dim=-1))

@@ -16,6 +16,8 @@
  *   dimsum_causal_conv1d_bwd    causal_conv1d_bwd() / causal_conv1d_bwd_cond()  causal_conv1d.cpp:349-427, :429-510
  *   dimsum_conv_xproj_fwd       causal_conv1d_fwd[_cond] + the x_proj F.linear + the B / C rearranges of MambaInnerFn*.forward,
  *                               mamba/mamba_ssm/ops/selective_scan_interface.py:836-866 (one tcgen05 kernel)
+ *   dimsum_attention_fwd        F.scaled_dot_product_attention at dimsum/attention_fusion.py:61-84 and in the shared DiTBlock
+ *                               (dimsum/models_dim.py:1532-1554), 256-token sequences, fp32 I/O with TF32 tensor cores
  *   dimsum_token_gather         torch.gather on token orders, mamba/mamba_ssm/modules/mamba_simple.py:634,657 and the
  *                               rearrange/flip/local_scan copies of dimsum/models_dim.py:1498-1524, :660-664,:700-701
  *   dimsum_wavelet_packet_fwd   WaveDiMBlock._dwt_fast  dimsum/models_dim.py:572-586 (+ local_scan :662)
@@ -187,6 +189,27 @@ typedef struct {
 } dimsum_conv_xproj_params;
 
 int dimsum_conv_xproj_fwd(const dimsum_conv_xproj_params *p, void *stream);
+
+/* ---- softmax attention (TMA + tcgen05, fp32 I/O, TF32 math, fp32 accumulation and softmax) -------------------------
+ * Replaces F.scaled_dot_product_attention(q, k, v) at dimsum/attention_fusion.py:61-84 (CrossAttentionFusion, 8 heads x 64)
+ * and in the shared DiTBlock (dimsum/models_dim.py:1532-1554, timm Attention, 16 heads x 64) for the 256-token sequences of
+ * the 256px configuration.  q, k, v: (batch, heads, seqlen, 64) views with innermost stride 1 and arbitrary positive,
+ * 16-byte aligned batch / head / token strides (the slices of a fused qkv projection are taken in place); out: written as
+ * out[b, h, token, :] with its own strides -- pass the strides of a (batch, tokens, heads * 64) buffer to get the layout the
+ * output projection reads.  No mask, no dropout (the model uses neither).  head_dim == 64, seqlen_k % 64 == 0, <= 256.
+ */
+typedef struct {
+    int64_t batch, heads, seqlen_q, seqlen_k, head_dim, dtype;
+    int64_t q_batch_stride, q_head_stride, q_token_stride;
+    int64_t k_batch_stride, k_head_stride, k_token_stride;
+    int64_t v_batch_stride, v_head_stride, v_token_stride;
+    int64_t out_batch_stride, out_head_stride, out_token_stride;
+    float scale;
+    const void *q, *k, *v;
+    void *out;
+} dimsum_attention_params;
+
+int dimsum_attention_fwd(const dimsum_attention_params *p, void *stream);
 
 /* ---- token-major gather: dst[b, l, :] = src[b, index[l], :]  for (batch, seqlen, channels) rows ---- */
 typedef struct {
