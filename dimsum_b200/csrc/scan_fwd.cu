@@ -41,7 +41,7 @@ struct ScanFwdArgs {
     const int32_t *perm;
     int64_t u_bs, u_ds, dl_bs, dl_ds, z_bs, z_ds, out_bs, out_ds, oz_bs, oz_ds;
     int64_t A_ds, A_ns, B_bs, B_gs, B_ns, C_bs, C_gs, C_ns;
-    int dim, seqlen, dstate, n_groups, n_chunks, softplus, vec_io, half_exp;
+    int dim, seqlen, dstate, n_groups, n_chunks, softplus, vec_io;
 };
 
 template <int LC, int kRows>
@@ -97,10 +97,9 @@ DEV void store_last_state(const ScanFwdArgs &a, int b, int d, const float2 (&h2)
     }
 }
 
-// kHalfExp (16-bit I/O only, experiment behind DIMSUM_SCAN_EX2_F16X2=1): decays from ex2.approx.ftz.f16x2, two per MUFU issue.
-// Measured and NOT the default: see profiles/r2_scan_fwd_experiments.md (an f16 decay has 11 significant bits, so a slow
-// state a = 0.999 is quantised to 0.9990 / 0.9995 and its memory length is off by tens of percent).
-template <typename T, bool kHasZ, bool kSoftplus, bool kArith, int kRows, bool kHalfExp = false>
+// (ex2.approx.f16x2 decays for 16-bit I/O were measured and rejected: two MUFU.EX2.F16 per packed op on sm_100a, slower, and
+// 3e-2 off on the reference test distribution -- profiles/r2_scan_fwd_experiments.md.)
+template <typename T, bool kHasZ, bool kSoftplus, bool kArith, int kRows>
 __global__ void __launch_bounds__(kRows, (sizeof(T) == 4 ? 4 : 3) * (128 / kRows)) scan_fwd_kernel(const ScanFwdArgs a) {
     constexpr int VEC = Io<T>::kVec;                 // elements per 16 bytes
     constexpr int LC = kRowBytes / (int)sizeof(T);   // steps per chunk: 16 (fp32) / 32 (16-bit)
@@ -260,18 +259,6 @@ __global__ void __launch_bounds__(kRows, (sizeof(T) == 4 ? 4 : 3) * (128 / kRows
                     dec[0] = make_float2(r, r2);
 #pragma unroll
                     for (int p = 1; p < kNS / 2; ++p) dec[p] = mul2(dec[p - 1], splat2(r2));
-                } else if (kHalfExp) {
-#pragma unroll
-                    for (int p = 0; p < kNS / 2; ++p) {
-                        const float2 t = mul2(splat2(dlt), A2[p]);
-                        uint32_t hx, he;
-                        asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hx) : "f"(t.y), "f"(t.x));
-                        asm("ex2.approx.f16x2 %0, %1;" : "=r"(he) : "r"(hx));
-                        float lo, hi;
-                        asm("{\n\t.reg .f16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}"
-                            : "=f"(lo), "=f"(hi) : "r"(he));
-                        dec[p] = make_float2(lo, hi);
-                    }
                 } else {
 #pragma unroll
                     for (int p = 0; p < kNS / 2; ++p) {
@@ -352,10 +339,10 @@ __global__ void __launch_bounds__(kRows, (sizeof(T) == 4 ? 4 : 3) * (128 / kRows
     if (a.x != nullptr && row_ok) store_last_state(a, b, d0 + tid, h2);
 }
 
-template <typename T, bool kHasZ, bool kSoftplus, bool kArith, int kRows, bool kHalfExp = false>
+template <typename T, bool kHasZ, bool kSoftplus, bool kArith, int kRows>
 int launch_rows(const ScanFwdArgs &a, int batch, cudaStream_t stream) {
     constexpr int LC = kRowBytes / (int)sizeof(T);
-    auto kern = scan_fwd_kernel<T, kHasZ, kSoftplus, kArith, kRows, kHalfExp>;
+    auto kern = scan_fwd_kernel<T, kHasZ, kSoftplus, kArith, kRows>;
     const int smem = (int)sizeof(ScanSmem<LC, kRows>);
     // per instantiation, one bit per device (the attribute is per device); atomic because autograd calls in from several threads
     static std::atomic<unsigned long long> configured{0};
@@ -406,9 +393,6 @@ int launch(const ScanFwdArgs &a, int batch, cudaStream_t stream) {
     bool half = wave_efficiency(n64, sms, 2 * per128) > wave_efficiency(n128, sms, per128) + 0.04;
     if (forced == 64) half = true;
     if (forced == 128) half = false;
-    if constexpr (sizeof(T) == 2 && !kArith && kHasZ && kSoftplus) {      // experiment hook, see kHalfExp
-        if (a.half_exp) return launch_rows<T, kHasZ, kSoftplus, kArith, 128, true>(a, batch, stream);
-    }
     return half ? launch_rows<T, kHasZ, kSoftplus, kArith, 64>(a, batch, stream)
                 : launch_rows<T, kHasZ, kSoftplus, kArith, 128>(a, batch, stream);
 }
@@ -475,10 +459,6 @@ extern "C" int dimsum_selective_scan_fwd(const dimsum_scan_fwd_params *p, void *
     a.dim = (int)p->dim; a.seqlen = (int)p->seqlen; a.dstate = (int)p->dstate; a.n_groups = (int)p->n_groups;
     a.n_chunks = (int)p->n_chunks;
     a.softplus = p->delta_softplus != 0;
-    {
-        static const int half_exp_env = [] { const char *e = getenv("DIMSUM_SCAN_EX2_F16X2"); return e ? atoi(e) : 0; }();
-        a.half_exp = half_exp_env;
-    }
 
     const int esz = p->io_dtype == DIMSUM_F32 ? 4 : 2;
     const int vec = 16 / esz;
