@@ -292,7 +292,12 @@ def run_train(args, rank, local_rank, world):
                                               "optimizer step" % sec}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # NCCL communicators that were captured into a CUDA graph do not tear down cleanly (destroy_process_group blocks):
+        # everything is printed and flushed, leave without the teardown
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 def run_b200(args, rank, local_rank, world):

@@ -158,8 +158,11 @@ def main():
                           "launch": "CUDA graph replay" if ts.graph is not None else "eager",
                           "loss": float(loss), "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30,
                           "missing_grads": ts.missing_grads()}))
-    if world > 1:
-        dist.destroy_process_group()
+    if world > 1:      # graph-captured NCCL communicators block in destroy_process_group: leave without the teardown
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
