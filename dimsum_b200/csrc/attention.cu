@@ -288,7 +288,9 @@ extern "C" int dimsum_attention_fwd(const dimsum_attention_params *p, void *stre
     int dev = 0;
     cudaGetDevice(&dev);
     if (!(configured.load(std::memory_order_acquire) >> (dev & 63) & 1ull)) {
-        cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        // the largest configuration (256 keys): 64 KB K + 64 KB V^T + 64 KB of Q buffers + alignment slack (static shared memory
+        // comes on top, so the 227 KB device limit itself is not a valid value here)
+        cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 65536 + 1024);
         configured.fetch_or(1ull << (dev & 63), std::memory_order_release);
     }
     dim3 grid((unsigned)p->heads, (unsigned)p->batch);

@@ -48,6 +48,7 @@ def main():
     ap.add_argument("--bwd", action="store_true", help="time the backward kernels at every shape (default: R <= 64)")
     ap.add_argument("--shapes", default=None, help="comma-separated RxDxL list replacing the default scan / conv shapes")
     ap.add_argument("--scan-only", action="store_true", help="only the scan / conv rows (skip wavelet, glue and gather kernels)")
+    ap.add_argument("--attention", action="store_true", help="with --scan-only: also time the attention kernel against the library SDPA")
     ap.add_argument("--tag", default="", help="free text appended to every printed row (experiment label)")
     args = ap.parse_args()
     from dimsum_b200 import causal_conv1d_cuda, selective_scan_cuda, wavelet_packet, scanning_orders as so
@@ -185,9 +186,28 @@ def main():
                                                            need_x=False, perm=perm), flush=flush)
         rows.append(dict(op="scan_fwd_infer_perm", dtype=str(dtype), R=Rr, D=Dd, L=L, ms=med, ms_best=best, gbs=by / med / 1e6, frac=by / med / 1e6 / pk))
         del xz, u, delta, Bm, Cm
+    if not args.scan_only or args.attention:
+        # attention at the model's shapes: 512 CFG rows, 256 tokens, 8 (fusion block) and 16 (DiT block) heads of 64, fp32 / TF32
+        from dimsum_b200.attention import attention
+        import torch.nn.functional as F
+        torch.backends.cuda.matmul.allow_tf32 = True
+        for H in (8, 16):
+            Bt, Nt = 512, 256
+            qkv = torch.randn(Bt, Nt, 3, H, 64, device="cuda")
+            q, k, v = qkv.permute(2, 0, 3, 1, 4).unbind(0)
+            by_a = 4 * 4 * Bt * H * Nt * 64                        # q, k, v read + out written once
+            fl = 4.0 * Bt * H * Nt * Nt * 64
+            with torch.no_grad():
+                med, best = timeit(lambda: attention(q, k, v), flush=flush)
+                rows.append(dict(op=f"attention_h{H}", dtype="torch.float32", R=Bt, D=H * 64, L=Nt, ms=med, ms_best=best,
+                                 gbs=by_a / med / 1e6, frac=by_a / med / 1e6 / pk, tflops=fl / med / 1e9))
+                med, best = timeit(lambda: F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(Bt, Nt, H * 64), flush=flush)
+                rows.append(dict(op=f"sdpa_lib_h{H}", dtype="torch.float32", R=Bt, D=H * 64, L=Nt, ms=med, ms_best=best,
+                                 gbs=by_a / med / 1e6, frac=by_a / med / 1e6 / pk, tflops=fl / med / 1e9))
     for r in rows:
         print(f"{r['op']:20s} {r['dtype']:15s} R={r['R']:4d} D={r['D']:5d} L={r['L']:5d}  {r['ms']:8.3f} ms (best {r['ms_best']:.3f})"
-              f"  {r['gbs']:8.1f} GB/s  {100 * r['frac']:5.1f}% of measured peak {pk:.0f} {args.tag}")
+              f"  {r['gbs']:8.1f} GB/s  {100 * r['frac']:5.1f}% of measured peak {pk:.0f} {args.tag}"
+              + (f"  {r['tflops']:.1f} TFLOP/s" if "tflops" in r else ""))
     if args.json:
         json.dump(rows, open(args.json, "w"), indent=1)
 
