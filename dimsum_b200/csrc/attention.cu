@@ -106,14 +106,26 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const AttnAr
     // 32 distinct banks (one 128-byte row, swizzled chunk = lane / 4)
     {
         const float *vb = a.v + (int64_t)b * a.v_bs + (int64_t)h * a.v_hs;
-        for (int item = warp; item < (nk / 32) * 16; item += kAttnThreads / 32) {
-            const int kb = item >> 4, q = item & 15;
-            const float4 v4 = *reinterpret_cast<const float4 *>(vb + (int64_t)(kb * 32 + lane) * a.v_ts + 4 * q);
-            unsigned char *blk = Vt + kb * 8192;
-            const float vals[4] = {v4.x, v4.y, v4.z, v4.w};
+        constexpr int kWarps = kAttnThreads / 32, kItems = (kMaxKeys / 32) * 16 / kWarps;      // <= 16 items per warp
+        const int n_items = (nk / 32) * 16;
+        float4 v4[kItems];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-                *reinterpret_cast<float *>(blk + umma::sw128_off(4 * q + i, lane >> 2) + (lane & 3) * 4) = vals[i];
+        for (int i = 0; i < kItems; ++i) {                       // all loads in flight before the first store
+            const int item = warp + i * kWarps;
+            if (item < n_items)
+                v4[i] = *reinterpret_cast<const float4 *>(vb + (int64_t)((item >> 4) * 32 + lane) * a.v_ts + 4 * (item & 15));
+        }
+#pragma unroll
+        for (int i = 0; i < kItems; ++i) {
+            const int item = warp + i * kWarps;
+            if (item < n_items) {
+                unsigned char *blk = Vt + (item >> 4) * 8192;
+                const int q = item & 15;
+                const float vals[4] = {v4[i].x, v4[i].y, v4[i].z, v4[i].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<float *>(blk + umma::sw128_off(4 * q + j, lane >> 2) + (lane & 3) * 4) = vals[j];
+            }
         }
     }
     umma::fence_smem_to_async();
