@@ -102,6 +102,22 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const AttnAr
             load_tile(Qs + t * q_buf + q_blk, &map_q, &bar_q[t], a.pos_q, 32, t * kQT, h, b);
         }
     }
+    const uint32_t idesc_s = umma::idesc(umma::kFmtTF32, kQT, nk);
+    const uint32_t idesc_o = umma::idesc(umma::kFmtTF32, kQT, kHd);
+    // S = Q K^T of query tile `qt` (one thread): 2 column blocks of head_dim x 4 K steps
+    auto issue_s = [&](int qt) {
+        const int buf = qt & 1;
+        umma::mbar_wait(&bar_q[buf], (qt >> 1) & 1);
+        umma::fence_after_sync();
+        const uint32_t sq = umma::smem_u32(Qs + buf * q_buf), sk = umma::smem_u32(Ks);
+#pragma unroll
+        for (int cb = 0; cb < 2; ++cb)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                umma::mma<true>(tmem, umma::desc_sw128(sq + cb * q_blk + k * 32), umma::desc_sw128(sk + cb * k_blk + k * 32), idesc_s,
+                                (cb | k) != 0);
+        umma::commit(&bar_s);
+    };
     // V^T: lane = key inside a 32-key column block, item = (column block, quad of head_dim); 4-byte stores of a warp fall in
     // 32 distinct banks (one 128-byte row, swizzled chunk = lane / 4)
     {
@@ -114,6 +130,10 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const AttnAr
             const int item = warp + i * kWarps;
             if (item < n_items)
                 v4[i] = *reinterpret_cast<const float4 *>(vb + (int64_t)((item >> 4) * 32 + lane) * a.v_ts + 4 * (item & 15));
+        }
+        if (tid == 0) {                                           // the tensor core starts on tile 0 while V^T is being stored
+            umma::mbar_wait(&bar_k, 0);
+            issue_s(0);
         }
 #pragma unroll
         for (int i = 0; i < kItems; ++i) {
@@ -131,27 +151,12 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const AttnAr
     umma::fence_smem_to_async();
     __syncthreads();
 
-    const uint32_t idesc_s = umma::idesc(umma::kFmtTF32, kQT, nk);
-    const uint32_t idesc_o = umma::idesc(umma::kFmtTF32, kQT, kHd);
     const int row = 32 * (warp & 3) + lane, half = warp >> 2;      // this thread's accumulator row and half of the columns
     const uint32_t lane_base = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
     const int cols_half = nk / 2;                                   // S columns per half (multiple of 32)
 
     for (int qt = 0; qt < n_qt; ++qt) {
         const int buf = qt & 1;
-        if (tid == 0) {
-            if (qt == 0) umma::mbar_wait(&bar_k, 0);
-            umma::mbar_wait(&bar_q[buf], (qt >> 1) & 1);
-            umma::fence_after_sync();
-            const uint32_t sq = umma::smem_u32(Qs + buf * q_buf), sk = umma::smem_u32(Ks);
-#pragma unroll
-            for (int cb = 0; cb < 2; ++cb)
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    umma::mma<true>(tmem, umma::desc_sw128(sq + cb * q_blk + k * 32), umma::desc_sw128(sk + cb * k_blk + k * 32), idesc_s,
-                                    (cb | k) != 0);
-            umma::commit(&bar_s);
-        }
         umma::mbar_wait(&bar_s, qt & 1);
         umma::fence_after_sync();
         if (tid == 0 && qt + 2 < n_qt) {                            // the Q buffer is free again: prefetch the tile after next
@@ -198,6 +203,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const AttnAr
         }
         umma::mbar_wait(&bar_o, qt & 1);
         umma::fence_after_sync();
+        if (tid == 0 && qt + 1 < n_qt) issue_s(qt + 1);            // P has been consumed: the next tile's S overlaps this epilogue
         // ---- epilogue: thread = (row, 32 of the 64 output columns)
         {
             uint32_t v[32];
@@ -213,10 +219,11 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const AttnAr
                                                                        __uint_as_float(v[j + 2]) * inv, __uint_as_float(v[j + 3]) * inv);
             }
         }
-        umma::fence_before_sync();
-        __syncthreads();                                            // S / P columns, red_* and O are free for the next tile
-        umma::fence_after_sync();
+        // no barrier here: the next tile's softmax synchronises the CTA before anything of this tile is overwritten
+        // (red_sum is rewritten after its __syncthreads, the O columns by an MMA issued after its second one)
     }
+    umma::fence_before_sync();
+    __syncthreads();
     if (warp == 0) umma::tmem_dealloc(tmem, 512);
 }
 
