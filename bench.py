@@ -30,6 +30,7 @@ NUM_GRID = 250
 D_INNER, D_STATE, SEQ = 1024, 16, 256
 RES = 32                         # latent side: 32 (256px, BASELINE configs[2]) or 64 (512px, configs[3]); --px sets RES and SEQ
 CPU_SAMPLE_LATENTS = 8          # bounded CPU sample: batching helps the CPU path (0.18 -> 0.57 latents/s from 1 to 8 on 8 cores)
+CPU_SAMPLE_CHOICES = (4, 8, 16)  # the reference arm tries these batch sizes once and times the best per-latent one
 
 
 def build_model(device, res=None, seed=0):
@@ -116,6 +117,35 @@ def measured_peak():
         return 6650.0, "fallback"
 
 
+def measure_scan_traffic(rows, dtype):
+    """DRAM bytes of ONE scan launch at this run's shape, measured now: a child process runs the launch under
+    `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` (tools/one_scan.py).  -> (bytes or None, how)."""
+    import shutil
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not os.path.exists(ncu):
+        return None, "ncu not found"
+    cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "-k", "regex:scan_fwd", "-c", "1",
+           "--csv", sys.executable, os.path.join(ROOT, "tools", "one_scan.py"), str(rows), str(D_INNER), str(SEQ), dtype]
+    try:
+        out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=240).stdout
+    except Exception as e:          # noqa: BLE001
+        return None, "ncu run failed: %s" % type(e).__name__
+    total, seen = 0.0, 0
+    for line in out.splitlines():
+        if "dram__bytes_" not in line:
+            continue
+        cols = [c.strip().strip('"') for c in line.split('","')]
+        try:
+            unit, val = cols[-2].lower(), float(cols[-1].replace(",", ""))
+        except (ValueError, IndexError):
+            continue
+        total += val * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(unit, 1)
+        seen += 1
+    if seen != 2:
+        return None, "could not parse the ncu output"
+    return int(total), "measured in this run: ncu dram__bytes_read.sum + dram__bytes_write.sum of one launch at this shape (tools/one_scan.py)"
+
+
 def scan_bytes(rows, s):
     """Algorithmic bytes of one inference scan launch: reads u, delta, z, B, C, A, D, dt_bias; writes y."""
     return s * (4 * rows * D_INNER * SEQ + 2 * rows * D_STATE * SEQ) + 4 * (D_INNER * D_STATE + 2 * D_INNER)
@@ -149,8 +179,11 @@ def run_reference(args, rank):
     torch.set_num_threads(os.cpu_count())
     model = build_model("cpu")
     sd = {k: v.detach() for k, v in model.state_dict().items()}
-    n = CPU_SAMPLE_LATENTS
-    for _ in range(args.warmup):
+    # the per-latent throughput of the CPU path depends on the batch: try a few sizes once (this doubles as warm-up) and time
+    # the best one, so the arm is not handicapped by an arbitrary sample size
+    tried = {c: c / cpu_reference_step(sd, c) for c in CPU_SAMPLE_CHOICES}
+    n = max(tried, key=tried.get)
+    for _ in range(max(0, args.warmup - 1)):
         cpu_reference_step(sd, n)
     times = [cpu_reference_step(sd, n) for _ in range(max(1, args.steps))]
     sec = sum(times) / len(times)
@@ -160,7 +193,8 @@ def run_reference(args, rank):
         "steps": len(times), "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args.latents), "impl": "reference CPU path (oracle port), bounded sample per step",
-                   "latents_per_step": n, "rows_per_step": 2 * n, "cfg_scale": CFG_SCALE, "tokens": SEQ, "px": 8 * RES},
+                   "latents_per_step": n, "rows_per_step": 2 * n, "cfg_scale": CFG_SCALE, "tokens": SEQ, "px": 8 * RES,
+                   "batch_sizes_tried_latents_per_s": {str(k): v for k, v in tried.items()}},
         "cpu_baseline": {"value": val, "unit": "latents/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": f"{n} latents ({2 * n} CFG rows) x {len(times)} evaluation(s) of the 249-evaluation sampler"},
         "e2e": {"value": val, "unit": "latents/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -481,7 +515,27 @@ def run_b200(args, rank, local_rank, world):
         with open(args.profile, "w") as f:
             f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=100))
 
+    gather_check = None
     if world > 1:
+        # the one data-path collective of the sampling design: sample_cfg_sharded's NCCL all_gather_into_tensor of the final
+        # latents (dimsum_b200/sampler.py).  Run it once here on hardware -- a short 3-point Euler grid over the same sharded
+        # batch -- and check every rank receives exactly the slices the ranks computed locally.
+        from dimsum_b200.sampler import sample_cfg, sample_cfg_sharded
+        zs, ys = z_all[: 8 * world].to(dev), y_all[: 8 * world].to(dev)
+        with autocast:
+            full = sample_cfg_sharded(model, zs, ys, cfg_scale=CFG_SCALE, num_steps=3)
+            mine = sample_cfg(model, zs[rank * 8:(rank + 1) * 8], ys[rank * 8:(rank + 1) * 8], cfg_scale=CFG_SCALE, num_steps=3)
+        same_local = torch.equal(full[rank * 8:(rank + 1) * 8], mine)
+        digest = full.double().sum().reshape(1)                    # identical on every rank iff every rank got every slice
+        lo_d, hi_d = digest.clone(), digest.clone()
+        dist.all_reduce(lo_d, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi_d, op=dist.ReduceOp.MAX)
+        flag = torch.tensor([int(same_local and bool(torch.isfinite(full).all()) and lo_d.item() == hi_d.item())], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        gather_check = {"collective": "NCCL all_gather_into_tensor of the final latents (sampler.sample_cfg_sharded)",
+                        "latents": 8 * world, "grid_points": 3, "bytes_gathered_per_rank": int(full.numel() * full.element_size()),
+                        "every_rank_holds_every_rank_local_result": bool(flag.item())}
+        assert flag.item() == 1, "sample_cfg_sharded: gathered latents differ from the rank-local results"
         tt = torch.tensor([ms, ms_e2e, scan_ms, fast_ms or 0.0], device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms, ms_e2e, scan_ms, fast_ms = tt.tolist()
@@ -495,14 +549,18 @@ def run_b200(args, rank, local_rank, world):
         peak, how = measured_peak()
         by = scan_bytes(2 * n, s)
         achieved = by / (scan_ms * 1e-3) / 1e9
-        traffic = None
-        tr_path = os.path.join(ROOT, "profiles", "scan_fwd_traffic.json")
-        if os.path.exists(tr_path) and RES == 32 and n == TOTAL_LATENTS:    # the capture was taken at this launch shape
-            try:
-                tr = json.load(open(tr_path))
-                traffic = tr.get(args.dtype, {}).get("dram_bytes_per_launch")
-            except Exception:
-                traffic = None
+        if world > 1:
+            traffic, traffic_how = None, "not measured in multi-rank runs (ncu is single-process only); see the 1-GPU line"
+        elif args.no_traffic:
+            traffic, traffic_how = None, "skipped (--no-traffic)"
+        else:
+            traffic, traffic_how = measure_scan_traffic(2 * n, args.dtype)
+        # the kernel's second ceiling: 20 MUFU results per element (16 decays + softplus 2 + silu 2) at the measured 16 per clock
+        # per SM (profiles/r1f_pipe_microbench.md) against the bytes per element at the HBM peak
+        elems = 2 * n * D_INNER * SEQ
+        sm_clock = 1e6 * (clocks.summary().get("sm_mhz") or 1965)
+        sfu_floor_ms = elems * 20 / 16 / 148 / sm_clock * 1e3
+        sfu_floor_ms_max_clock = elems * 20 / 16 / 148 / 1.965e9 * 1e3
         line = {
             "metric": "DiMSUM-L/2 fwd latents/s", "value": n_total / (ms * 1e-3), "unit": "latents/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
@@ -520,7 +578,15 @@ def run_b200(args, rank, local_rank, world):
             "gpu_launches": launches,
             "roofline": {"kernel": "scan_fwd_kernel (selective scan forward, inference)", "bound": "hbm",
                          "achieved": achieved, "peak": peak, "peak_source": how + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes_per_launch": by,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_how,
+                         "algorithmic_bytes_per_launch": by,
+                         "sfu_ceiling": {"mufu_results_per_element": 20, "mufu_results_per_clk_per_sm": 16,
+                                         "floor_ms_at_step_clock": sfu_floor_ms, "frac_of_sfu_ceiling_in_step": sfu_floor_ms / scan_ms,
+                                         "floor_ms_at_max_clock": sfu_floor_ms_max_clock,
+                                         "hbm_frac_at_sfu_ceiling": by / (sfu_floor_ms_max_clock * 1e-3) / 1e9 / peak,
+                                         "note": "general A needs 20 MUFU results per element; the kernel is bound by the SFU pipe, "
+                                                 "not by HBM (ncu: XU pipe 84.5 % busy, profiles/r1e_scan_fwd_ncu.md); `frac` is "
+                                                 "against HBM as the contract asks, this block gives the fraction of the binding unit"},
                          "avg_launch_ms": scan_ms, "launches_timed": n_general,
                          "isolated": None if iso_ms is None else
                              {"avg_launch_ms": iso_ms, "frac": by / (iso_ms * 1e-3) / 1e9 / peak,
@@ -537,6 +603,8 @@ def run_b200(args, rank, local_rank, world):
                          "share_of_step": scan_ms * 32 / ms},
             "clocks": clocks.summary(),
         }
+        if gather_check is not None:
+            line["all_gather_check"] = gather_check
         if world == 1 and not args.no_cpu_baseline:
             torch.set_num_threads(os.cpu_count())
             sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
@@ -564,6 +632,7 @@ def main():
     ap.add_argument("--latents", type=int, default=TOTAL_LATENTS)
     ap.add_argument("--px", type=int, default=256, choices=[256, 512], help="image size: 256 (L=256 tokens) or 512 (L=1024, configs[3])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-traffic", action="store_true", help="skip the in-run ncu measurement of the scan's DRAM traffic (~30 s)")
     ap.add_argument("--profile", default=None,
                     help="also write a torch.profiler kernel table of two eager steps to this file (after all timing)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying a CUDA graph")
