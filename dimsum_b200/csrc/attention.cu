@@ -143,8 +143,9 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const AttnAr
                 const int q = item & 15;
                 const float vals[4] = {v4[i].x, v4[i].y, v4[i].z, v4[i].w};
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    *reinterpret_cast<float *>(blk + umma::sw128_off(4 * q + j, lane >> 2) + (lane & 3) * 4) = vals[j];
+                for (int j = 0; j < 4; ++j)              // rounded to nearest tf32 on the way (the tensor core would truncate)
+                    *reinterpret_cast<uint32_t *>(blk + umma::sw128_off(4 * q + j, lane >> 2) + (lane & 3) * 4) =
+                        (__float_as_uint(vals[j]) + 0x1000u) & 0xffffe000u;
             }
         }
     }
@@ -183,9 +184,12 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const AttnAr
             umma::tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
+                // the tensor core TRUNCATES fp32 operands to tf32, which would bias every probability low (2.4e-3 on the output
+                // against 5e-4 with rounding): round to nearest here, and normalise by the sum of the ROUNDED values
                 const float p = ex2_mufu(fmaf(__uint_as_float(v[j]), a.scale_log2e, -m));
-                sum += p;
-                v[j] = __float_as_uint(p);
+                const uint32_t pr = (__float_as_uint(p) + 0x1000u) & 0xffffe000u;
+                sum += __uint_as_float(pr);
+                v[j] = pr;
             }
             umma::tmem_st32(lane_base + half * cols_half + c0, v);
         }

@@ -30,15 +30,16 @@ def test_attention_matches_fp64_softmax_attention(B, H, Nq, Nk):
     from dimsum_b200.attention import attention, attention_supported
     g = torch.Generator(device="cuda").manual_seed(B * 1000 + Nq)
     # q / k / v as the slices of fused qkv projections (the model's layout: (B, N, 3, H, 64) permuted), large logits included
-    qkv_q = torch.randn(B, Nq, 3, H, 64, generator=g, device="cuda") * 1.5
-    qkv_k = torch.randn(B, Nk, 3, H, 64, generator=g, device="cuda") * 1.5
+    scale = 1.5 if B % 2 else 1.0                      # sharp and flat softmax rows
+    qkv_q = torch.randn(B, Nq, 3, H, 64, generator=g, device="cuda") * scale
+    qkv_k = torch.randn(B, Nk, 3, H, 64, generator=g, device="cuda") * scale
     q = qkv_q.permute(2, 0, 3, 1, 4)[0]
     k, v = qkv_k.permute(2, 0, 3, 1, 4)[1], qkv_k.permute(2, 0, 3, 1, 4)[2]
     with torch.no_grad():
         assert attention_supported(q, k, v)
         got = attention(q, k, v)
         assert got.shape == (B, Nq, H * 64)
-        assert rel_err(got, _ref(q, k, v).float()) <= 2e-3, rel_err(got, _ref(q, k, v).float())
+        assert rel_err(got, _ref(q, k, v).float()) <= 1.5e-3, rel_err(got, _ref(q, k, v).float())
         # writing into one half of a wider buffer (CrossAttentionFusion: no cat copy)
         both = torch.full((B, Nq, 2 * H * 64), 9.0, device="cuda")
         attention(q, k, v, out=both[:, :, H * 64:].view(B, Nq, H, 64))
