@@ -39,7 +39,7 @@ def test_attention_matches_fp64_softmax_attention(B, H, Nq, Nk):
         assert attention_supported(q, k, v)
         got = attention(q, k, v)
         assert got.shape == (B, Nq, H * 64)
-        assert rel_err(got, _ref(q, k, v).float()) <= 1.5e-3, rel_err(got, _ref(q, k, v).float())
+        assert rel_err(got, _ref(q, k, v).float()) <= 2e-3, rel_err(got, _ref(q, k, v).float())
         # writing into one half of a wider buffer (CrossAttentionFusion: no cat copy)
         both = torch.full((B, Nq, 2 * H * 64), 9.0, device="cuda")
         attention(q, k, v, out=both[:, :, H * 64:].view(B, Nq, H, 64))
