@@ -396,6 +396,18 @@ def run_b200(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
+    if args.ncu_range:
+        x = x0.clone()
+        for i in range(args.warmup):
+            x = eager_step(x, i)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        x = eager_step(x, args.warmup)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        print("ncu range done (no bench line: profiler runs are not measurements)")
+        return
+
     # ------------------------------------------------------------------ device-resident timing
     with ClockSampler(local_rank) as clocks:       # nvidia-smi is started before the warm-up so it is sampling by the time
         x = x0.clone()                             # the timed region starts; only samples inside the region are reported
@@ -635,6 +647,9 @@ def main():
     ap.add_argument("--no-traffic", action="store_true", help="skip the in-run ncu measurement of the scan's DRAM traffic (~30 s)")
     ap.add_argument("--profile", default=None,
                     help="also write a torch.profiler kernel table of two eager steps to this file (after all timing)")
+    ap.add_argument("--ncu-range", action="store_true",
+                    help="for `ncu --profile-from-start off`: warm up, then bracket ONE eager step with cudaProfilerStart/Stop and exit "
+                         "(launch lists under profiles/; numbers printed under a profiler are never bench values)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying a CUDA graph")
     ap.add_argument("--init-form-fastpath", action="store_true",
                     help="let the scan use its one-exp-per-step path for arithmetic-progression A.  The random-init benchmark "

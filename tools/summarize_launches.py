@@ -29,7 +29,9 @@ def main():
         agg[short][1] += v
         n += 1
     tot = sum(v[1] for v in agg.values())
-    ours = sum(v[1] for k, v in agg.items() if "dimsum" in k or any(t in k for t in ("scan_fwd", "scan_bwd", "conv_fwd", "conv_bwd", "wavelet_kernel", "gather_kernel", "rowwise_kernel", "add_rmsnorm")))
+    mine = ("scan_fwd", "scan_bwd", "conv_fwd", "conv_bwd", "conv_xproj", "attention_kernel", "wavelet_kernel", "gather_kernel",
+            "rowwise_kernel", "add_rmsnorm", "norm_kernel", "gelu_mul", "colsum", "rmsnorm_bwd")
+    ours = sum(v[1] for k, v in agg.items() if "dimsum" in k or any(t in k for t in mine))
     print(f"launches: {n}   total device time: {tot / 1e3:.1f} ms   this repo's kernels: {100 * ours / tot:.1f} % of device time\n")
     print("| share | launches | avg us | kernel |")
     print("|---:|---:|---:|---|")
