@@ -224,7 +224,8 @@ def run_train(args, rank, local_rank, world):
     rank, local_rank, world, dev = init_dist()
     torch.backends.cuda.matmul.allow_tf32 = True
     B = args.train_batch
-    ts = TrainStep(dev, rank, world, B, "bf16" if args.dtype != "fp32" else "fp32", use_graph=not args.no_graph)
+    ts = TrainStep(dev, rank, world, B, "bf16" if args.dtype != "fp32" else "fp32", use_graph=not args.no_graph,
+                   bucket_mb=args.bucket_mb)
 
     def barrier():
         if world > 1:
@@ -300,7 +301,7 @@ def run_train(args, rank, local_rank, world):
             "vs_baseline": None, "dtype": "bf16" if args.dtype != "fp32" else "f32", "data": "synthetic",
             "config": {"workload": "DiMSUM-L/2 bf16 training step on synthetic latents (BASELINE configs[4]): %d latents per GPU, GVP "
                                    "velocity loss, DDP gradient all-reduce over NCCL, clip 1.0, fused AdamW lr 1e-4" % B,
-                       "per_gpu_batch": B, "tokens": SEQ, "d_inner": D_INNER, "d_state": D_STATE,
+                       "per_gpu_batch": B, "ddp_bucket_mb": args.bucket_mb, "tokens": SEQ, "d_inner": D_INNER, "d_state": D_STATE,
                        "launch": "eager" if ts.graph is None else "one CUDA graph per step (forward, backward with DDP's bucketed NCCL "
                                  "all-reduces, clip, AdamW)",
                        "l2": "activations of one step >> 126 MB L2", "params": sum(p.numel() for p in ts.model.parameters()),
@@ -641,6 +642,7 @@ def main():
     ap.add_argument("--workload", default="sample", choices=["sample", "train"],
                     help="sample: CFG denoising evaluation (BASELINE configs[2], the headline); train: bf16 DDP training step (configs[4])")
     ap.add_argument("--train-batch", type=int, default=32, help="per-GPU batch of --workload train (SURVEY.md 8d config 5)")
+    ap.add_argument("--bucket-mb", type=int, default=25, help="DDP gradient bucket size of --workload train (MB)")
     ap.add_argument("--latents", type=int, default=TOTAL_LATENTS)
     ap.add_argument("--px", type=int, default=256, choices=[256, 512], help="image size: 256 (L=256 tokens) or 512 (L=1024, configs[3])")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -38,7 +38,8 @@ class TrainStep:
     """One optimizer step of config 5 on this rank's GPU: `step()` draws a synthetic batch on the device and runs (or
     replays) forward + backward (+ DDP all-reduce) + clip + AdamW; returns the loss tensor."""
 
-    def __init__(self, dev, rank, world, batch=32, dtype="bf16", model_name="DiM-L/2", depth=None, use_graph=True, res=32):
+    def __init__(self, dev, rank, world, batch=32, dtype="bf16", model_name="DiM-L/2", depth=None, use_graph=True, res=32,
+                 bucket_mb=25):
         from dimsum_b200.models_dim import DiM, DiM_models
         self.dev, self.rank, self.world, self.batch, self.res = dev, rank, world, batch, res
         torch.manual_seed(0)
@@ -59,7 +60,8 @@ class TrainStep:
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             # DDP is constructed on the side stream so that its bucket streams / events are captured consistently
-            self.ddp = (torch.nn.parallel.DistributedDataParallel(self.model, device_ids=[dev.index], gradient_as_bucket_view=True)
+            self.ddp = (torch.nn.parallel.DistributedDataParallel(self.model, device_ids=[dev.index], gradient_as_bucket_view=True,
+                                                                  bucket_cap_mb=bucket_mb)
                         if world > 1 else self.model)
             self.opt = torch.optim.AdamW(self.model.parameters(), lr=1e-4, weight_decay=0, capturable=use_graph, fused=True)
             if use_graph:
