@@ -642,7 +642,7 @@ def main():
     ap.add_argument("--workload", default="sample", choices=["sample", "train"],
                     help="sample: CFG denoising evaluation (BASELINE configs[2], the headline); train: bf16 DDP training step (configs[4])")
     ap.add_argument("--train-batch", type=int, default=32, help="per-GPU batch of --workload train (SURVEY.md 8d config 5)")
-    ap.add_argument("--bucket-mb", type=int, default=25, help="DDP gradient bucket size of --workload train (MB)")
+    ap.add_argument("--bucket-mb", type=int, default=100, help="DDP gradient bucket size of --workload train (MB)")
     ap.add_argument("--latents", type=int, default=TOTAL_LATENTS)
     ap.add_argument("--px", type=int, default=256, choices=[256, 512], help="image size: 256 (L=256 tokens) or 512 (L=1024, configs[3])")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -39,7 +39,7 @@ class TrainStep:
     replays) forward + backward (+ DDP all-reduce) + clip + AdamW; returns the loss tensor."""
 
     def __init__(self, dev, rank, world, batch=32, dtype="bf16", model_name="DiM-L/2", depth=None, use_graph=True, res=32,
-                 bucket_mb=25):
+                 bucket_mb=100):
         from dimsum_b200.models_dim import DiM, DiM_models
         self.dev, self.rank, self.world, self.batch, self.res = dev, rank, world, batch, res
         torch.manual_seed(0)
