@@ -116,6 +116,7 @@ RowwiseParams = STRUCTS["dimsum_rowwise_params"]
 RmsnormParams = STRUCTS["dimsum_rmsnorm_params"]
 GeluMulParams = STRUCTS["dimsum_gelu_mul_params"]
 NormModulateParams = STRUCTS["dimsum_norm_modulate_params"]
+CfgEulerParams = STRUCTS["dimsum_cfg_euler_params"]
 ColsumParams = STRUCTS["dimsum_colsum_params"]
 GeluMulBwdParams = STRUCTS["dimsum_gelu_mul_bwd_params"]
 RmsnormBwdParams = STRUCTS["dimsum_rmsnorm_bwd_params"]
@@ -135,6 +136,7 @@ ENTRY_POINTS = {
     "dimsum_add_rmsnorm": RmsnormParams,
     "dimsum_gelu_mul": GeluMulParams,
     "dimsum_norm_modulate": NormModulateParams,
+    "dimsum_cfg_euler_step": CfgEulerParams,
     "dimsum_token_colsum": ColsumParams,
     "dimsum_gelu_mul_bwd": GeluMulBwdParams,
     "dimsum_add_rmsnorm_bwd": RmsnormBwdParams,

@@ -227,6 +227,33 @@ __global__ void __launch_bounds__(256) gelu_mul_kernel(const dimsum_gelu_mul_par
     }
 }
 
+// CFG combine + Euler update of the sampler in one pass: v = uncond + s (cond - uncond) on the first `channels` channels of the
+// model output, x_new = x + dt v for BOTH halves of the CFG batch (they stay identical copies, sample_ddp.py:168-173).
+// Arithmetic order and roundings are those of the PyTorch expressions it replaces (no FMA contraction).
+template <typename T>
+__global__ void __launch_bounds__(256) cfg_euler_kernel(const dimsum_cfg_euler_params p) {
+    const int64_t i4 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int64_t per_row = p.channels * p.hw;                  // elements of one latent (guided channels only)
+    if (i4 >= p.half_batch * per_row) return;
+    const int64_t r = i4 / per_row, e = i4 - r * per_row;
+    const T *oc = reinterpret_cast<const T *>(p.model_out) + r * p.out_row_stride + e;
+    const T *ou = oc + p.half_batch * p.out_row_stride;
+    float c[4], u[4], x[4], o[4];
+    Io<T>::ld4(oc, c);
+    Io<T>::ld4(ou, u);
+    const float *xp = reinterpret_cast<const float *>(p.x) + r * per_row + e;
+    *reinterpret_cast<float4 *>(x) = *reinterpret_cast<const float4 *>(xp);
+    const float dt = *p.dt, s = p.cfg_scale;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float v = __fadd_rn(u[i], __fmul_rn(s, __fsub_rn(c[i], u[i])));
+        o[i] = __fadd_rn(x[i], __fmul_rn(dt, v));
+    }
+    float *d0 = reinterpret_cast<float *>(p.x_new) + r * per_row + e;
+    *reinterpret_cast<float4 *>(d0) = *reinterpret_cast<const float4 *>(o);
+    *reinterpret_cast<float4 *>(d0 + p.half_batch * per_row) = *reinterpret_cast<const float4 *>(o);
+}
+
 // column sums over the tokens of a batch row: CTA = (128 channels, batch row); 8 warps stride over the tokens, a lane
 // owns 4 consecutive channels, partial sums meet in shared memory
 __global__ void __launch_bounds__(256) colsum_kernel(const dimsum_colsum_params p) {
@@ -456,6 +483,23 @@ extern "C" int dimsum_gelu_mul(const dimsum_gelu_mul_params *p, void *stream_) {
     else { GM(__half) }
 #undef GM
     return check_launch("gelu_mul");
+}
+
+extern "C" int dimsum_cfg_euler_step(const dimsum_cfg_euler_params *p, void *stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (p != nullptr && p->half_batch == 0) return DIMSUM_OK;
+    DIMSUM_REQUIRE(p != nullptr && p->model_out && p->x && p->x_new && p->dt, DIMSUM_ERR_INVALID, "cfg_euler_step: null pointer");
+    DIMSUM_REQUIRE(p->half_batch > 0 && p->channels > 0 && p->hw > 0 && p->out_dtype >= 0 && p->out_dtype <= 2, DIMSUM_ERR_INVALID,
+                   "cfg_euler_step: bad arguments");
+    DIMSUM_REQUIRE((p->channels * p->hw) % 4 == 0 && p->out_row_stride % 4 == 0 && aligned16(p->x) && aligned16(p->x_new) &&
+                       (reinterpret_cast<uintptr_t>(p->model_out) & (p->out_dtype == DIMSUM_F32 ? 15u : 7u)) == 0,
+                   DIMSUM_ERR_UNSUPPORTED, "cfg_euler_step: latents must be 16-byte aligned with a multiple of 4 elements");
+    const int64_t total = p->half_batch * p->channels * p->hw / 4;
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    if (p->out_dtype == DIMSUM_F32) cfg_euler_kernel<float><<<blocks, 256, 0, stream>>>(*p);
+    else if (p->out_dtype == DIMSUM_BF16) cfg_euler_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(*p);
+    else cfg_euler_kernel<__half><<<blocks, 256, 0, stream>>>(*p);
+    return check_launch("cfg_euler_step");
 }
 
 extern "C" int dimsum_token_colsum(const dimsum_colsum_params *p, void *stream_) {

@@ -149,6 +149,25 @@ def gelu_mul(x12):
     return y.view(shape[:-1] + (H,))
 
 
+def cfg_euler_step(x, model_out, cfg_scale, dt, out=None):
+    """x_new = x + dt * (uncond + s * (cond - uncond)) on both halves of a CFG batch, one pass (models_dim.py:1886-1902 +
+    integrators.py:98-111).  x (2n, C, H, W) fp32; model_out (2n, >= C, H, W), cond rows first; dt: fp32 CUDA scalar tensor."""
+    n2, C, H, W = x.shape
+    if (x.dtype != torch.float32 or not x.is_contiguous() or model_out.shape[0] != n2 or n2 % 2 or model_out.shape[1] < C
+            or model_out.shape[2:] != x.shape[2:] or model_out.dtype not in _DT or model_out[0].numel() != model_out.stride(0)
+            or dt.dtype != torch.float32 or not dt.is_cuda or dt.numel() != 1):
+        raise RuntimeError("cfg_euler_step: x must be contiguous fp32 (2n, C, H, W), model_out (2n, >= C, H, W) with dense rows, dt an "
+                           "fp32 CUDA scalar")
+    out = torch.empty_like(x) if out is None else out
+    with torch.cuda.device(x.device):
+        p = _lib.CfgEulerParams()
+        p.half_batch, p.channels, p.hw, p.out_dtype, p.out_row_stride = n2 // 2, C, H * W, _DT[model_out.dtype], model_out.stride(0)
+        p.cfg_scale = float(cfg_scale)
+        p.model_out, p.x, p.dt, p.x_new = model_out.data_ptr(), x.data_ptr(), dt.data_ptr(), out.data_ptr()
+        _lib.call("dimsum_cfg_euler_step", p, torch.cuda.current_stream(x.device).cuda_stream)
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------
 # training: the same kernels under autograd
 # ---------------------------------------------------------------------------------------------------

@@ -30,16 +30,22 @@ def sample_cfg(model, z, y, cfg_scale=4.0, num_steps=250, null_class=None, use_g
     x = torch.cat([z, z], dim=0)
     yy = torch.cat([y, torch.full_like(y, null_class)], dim=0)
     if use_graph and x.is_cuda:
+        # one graph replay per grid point: model forward + fused CFG combine + Euler update (x stays in the graph's buffer)
         step = GraphedCfgStep(model, x, yy, cfg_scale)
-        drift = lambda xx, tt: step(xx, tt)
-    else:
-        drift = lambda xx, tt: model.forward_with_cfg(xx, tt, yy, cfg_scale=cfg_scale)
+        ts = torch.linspace(0.0, 1.0, num_steps, device=x.device)
+        ones = torch.ones(x.shape[0], device=x.device)
+        for i in range(num_steps - 1):
+            x = step.euler(x, ones * ts[i], ts[i + 1] - ts[i])
+        return x[: len(z)].clone()
+    drift = lambda xx, tt: model.forward_with_cfg(xx, tt, yy, cfg_scale=cfg_scale)
     x = euler_velocity_ode(drift, x, num_steps)
     return x[: len(z)]
 
 
 class GraphedCfgStep:
-    """One CFG denoising evaluation v = model.forward_with_cfg(x, t, y) captured as a CUDA graph and replayed.
+    """One CFG denoising evaluation captured as a CUDA graph and replayed: the model forward on the doubled batch plus, for fp32
+    latents, ONE kernel of this repo for the guidance combine and the Euler update (`euler()`); `__call__` returns the drift
+    v = model.forward_with_cfg(x, t, y).
 
     The ~3000 kernel launches of a DiM-L/2 forward cost more host time than device time once the per-rank batch is
     small (8-GPU sharding), so the sampler replays a captured graph: static input buffers, one `cudaGraphLaunch` per
@@ -60,15 +66,51 @@ class GraphedCfgStep:
         from . import _lib
         before = _lib.launch_count()
         self.graph = torch.cuda.CUDAGraph()
+        self.dt = torch.zeros((), device=x_example.device)
+        self.x_new = torch.empty_like(self.x)
+        fused_ok = (self.x.dtype == torch.float32 and self.x.dim() == 4 and not getattr(model, "learn_sigma", False)
+                    and self.x[0].numel() % 4 == 0)
         with torch.cuda.graph(self.graph), torch.no_grad(), amp():
-            self.v = model.forward_with_cfg(self.x, self.t, self.y, cfg_scale=cfg_scale)
+            if fused_ok:
+                # forward_with_cfg (models_dim.py:1886-1902) = forward on [half, half] + the guidance combine; the combine and
+                # the Euler update run as ONE kernel of this repo inside the graph (dimsum_cfg_euler_step)
+                from . import fused
+                half = self.x[: len(self.x) // 2]
+                out = model.forward(torch.cat([half, half], dim=0), self.t, self.y)
+                fused.cfg_euler_step(self.x, out, cfg_scale, self.dt, out=self.x_new)
+                self.v = None
+            else:
+                self.v = model.forward_with_cfg(self.x, self.t, self.y, cfg_scale=cfg_scale)
+        self.fused = fused_ok
+        self.cfg_scale = cfg_scale
+        self.model = model
         self.launches_per_replay = _lib.launch_count() - before
 
     def __call__(self, x, t):
+        """-> v = forward_with_cfg(x, t, y) (the drift).  With the fused graph the drift is recovered from the Euler update."""
+        if self.fused:
+            one = torch.ones((), device=self.x.device)
+            return self.euler(x, t, one) - x
         self.x.copy_(x, non_blocking=True)
         self.t.copy_(t, non_blocking=True)
         self.graph.replay()
         return self.v
+
+    def euler(self, x, t, dt):
+        """-> x + dt * forward_with_cfg(x, t, y): one graph replay (the returned tensor is the graph's buffer, valid until the
+        next replay)."""
+        if x.data_ptr() != self.x.data_ptr():
+            self.x.copy_(x, non_blocking=True)
+        self.t.copy_(t, non_blocking=True)
+        if not self.fused:
+            self.graph.replay()
+            return x + dt * self.v.float()
+        if torch.is_tensor(dt):
+            self.dt.copy_(dt, non_blocking=True)
+        else:
+            self.dt.fill_(float(dt))
+        self.graph.replay()
+        return self.x_new                            # the graph reads self.x and writes self.x_new (static buffers)
 
 
 def shard_batch(n_total, rank, world):

@@ -313,6 +313,23 @@ typedef struct {
 
 int dimsum_gelu_mul(const dimsum_gelu_mul_params *p, void *stream);
 
+/* Sampler step: classifier-free-guidance combine of DiM.forward_with_cfg (dimsum/models_dim.py:1886-1902:
+ * half = uncond + s (cond - uncond) on the first `channels` channels, the two halves of the batch made identical) fused with
+ * the fixed-grid Euler update of the velocity ODE (dimsum/transport/integrators.py:98-111: x += dt v).
+ *   model_out : (2 * half_batch, >= channels, H, W) in out_dtype, row (sample) stride out_row_stride; cond rows first
+ *   x, x_new  : (2 * half_batch, channels, H, W) fp32 contiguous (x_new may alias x); dt: fp32 scalar in DEVICE memory (so the
+ *               step can sit inside a CUDA graph whose grid position changes between replays)
+ */
+typedef struct {
+    int64_t half_batch, channels, hw, out_dtype, out_row_stride;
+    float cfg_scale;
+    const void *model_out, *x;
+    const float *dt;
+    void *x_new;
+} dimsum_cfg_euler_params;
+
+int dimsum_cfg_euler_step(const dimsum_cfg_euler_params *p, void *stream);
+
 /* ---- backward pieces of the glue (training) ------------------------------------------------ */
 /* Column sums over the tokens of each batch row, the reductions autograd needs for adaLN modulate / gated residual
  * (d shift = sum_l g, d scale = sum_l g x, d gate = sum_l g m; reference: autograd through models_dim.py:34-35, 1509-1512):

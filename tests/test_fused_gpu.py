@@ -213,3 +213,25 @@ def test_gate_residual_fn_small_bf16_gates_keep_their_gradient(x_dtype):
     want_gate = (gy.float() * m.detach().float()).sum(1)
     assert rel_err(gate.grad, want_gate) <= 1e-2
     assert rel_err(x.grad, gy) <= 1e-6
+
+
+@pytest.mark.parametrize("out_dtype", [torch.float32, torch.bfloat16])
+def test_cfg_euler_step_matches_forward_with_cfg_plus_euler(out_dtype):
+    """dimsum_cfg_euler_step == the guidance combine of DiM.forward_with_cfg (models_dim.py:1886-1902) followed by the fixed-grid
+    Euler update (integrators.py:98-111), bit for bit in fp32 (same order of roundings)."""
+    from dimsum_b200 import fused
+    g = torch.Generator(device="cuda").manual_seed(8)
+    n, C, H = 6, 4, 32
+    half = torch.randn(n, C, H, H, generator=g, device="cuda")
+    x = torch.cat([half, half])
+    out = torch.randn(2 * n, C, H, H, generator=g, device="cuda").to(out_dtype)
+    dt = torch.tensor(1.0 / 249, device="cuda")
+    got = fused.cfg_euler_step(x, out, 4.0, dt)
+    o = out.float()
+    cond, uncond = o[:n], o[n:]
+    v = uncond + 4.0 * (cond - uncond)
+    want = x + dt * torch.cat([v, v])
+    assert torch.equal(got, want)
+    assert torch.equal(got[:n], got[n:])
+    with pytest.raises(RuntimeError):
+        fused.cfg_euler_step(x.half(), out, 4.0, dt)
