@@ -3,8 +3,9 @@
 Reference call sites: `F.scaled_dot_product_attention(q, k, v)` in dimsum/attention_fusion.py:61-84 and the timm `Attention`
 of the shared DiTBlock (dimsum/models_dim.py:1532-1554).  fp32 tensors, TF32 tensor-core products with fp32 accumulation and
 an fp32 softmax -- the precision class cuBLAS uses for the surrounding GEMMs when `torch.backends.cuda.matmul.allow_tf32` is
-on, which is the condition for taking this path.  Forward only: recorded (training) passes, 16-bit autocast and sequences
-beyond 256 tokens keep the library SDPA (a library GPU kernel, not a fallback of this repo's hot path).
+on, which is the condition for taking this path.  Up to 256 keys one CTA per (batch, head) keeps K and V^T on chip for both query
+tiles; longer sequences (512px: 1024 tokens) walk the keys in blocks of 256 with the online softmax.  Forward only: recorded
+(training) passes and 16-bit autocast keep the library SDPA (a library GPU kernel, not a fallback of this repo's hot path).
 """
 import os
 
@@ -20,7 +21,7 @@ def attention_supported(q, k, v):
         return False
     B, H, Nq, d = q.shape
     Nk = k.shape[2]
-    if d != 64 or k.shape != (B, H, Nk, d) or v.shape != k.shape or Nk % 64 or Nk > 256 or B > 65535 or H > 65535:
+    if d != 64 or k.shape != (B, H, Nk, d) or v.shape != k.shape or Nk % 64 or B > 65535 or H > 65535:
         return False
     for t in (q, k, v):
         if t.stride(3) != 1 or t.data_ptr() % 16 or any(s <= 0 or s % 4 for s in t.stride()[:3]):

@@ -6,7 +6,7 @@
 // fp32 sampling step the library kernel PyTorch picks for fp32 (`fmha_cutlassF_f32_aligned_64x64_rf_sm80`, an Ampere
 // kernel) was 24 % of the device time.
 //
-// One CTA per (batch, head).  K (all <= 256 keys, two 128-byte column blocks of head_dim) and the query tiles arrive by TMA
+// Up to 256 keys: one CTA per (batch, head).  K (all <= 256 keys, two 128-byte column blocks of head_dim) and the query tiles arrive by TMA
 // in the tensor core's SWIZZLE_128B K-major layout; V is transposed on the way in (V^T is the K-major B operand of P V;
 // kind::tf32 has no MN-major mode) with conflict-free 4-byte stores.  Per 128-query tile:
 //   S = Q K^T      8 tcgen05.mma (M 128, N = keys, K 8) into TMEM columns [0, keys)
@@ -231,6 +231,172 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const AttnAr
     if (warp == 0) umma::tmem_dealloc(tmem, 512);
 }
 
+
+// ---- sequences beyond 256 keys (512px configuration: 1024 tokens) -------------------------------------------------------------
+// One CTA per (batch, head, 128-query tile); the keys are walked in blocks of up to 256 with the online softmax: running row max
+// m and row sum l per thread, p = 2^(s c - m_new), l = l 2^(m - m_new) + sum p, and the O accumulator (TMEM) rescaled by
+// 2^(m - m_new) with tcgen05.ld / st before the block's P V is accumulated on top.  K blocks arrive by TMA (the next one is
+// requested as soon as this block's S = Q K^T has been computed), V blocks are transposed on the way in as above.
+__global__ void __launch_bounds__(kAttnThreads, 1) attention_long_kernel(const AttnArgs a, const __grid_constant__ CUtensorMap map_q,
+                                                                         const __grid_constant__ CUtensorMap map_k) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ uint64_t bar_k, bar_q, bar_s, bar_o;
+    __shared__ uint32_t tmem_slot;
+    __shared__ float red_max[2][kQT], red_sum[2][kQT];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    constexpr uint32_t k_blk = kMaxKeys * 128;                  // one column block of a 256-key K block
+    unsigned char *Ks = smem;                                   // [2 column blocks of head_dim][256 rows][128 B]
+    unsigned char *Vt = Ks + 2 * k_blk;                         // [8 column blocks of 32 keys][64 rows][128 B]
+    unsigned char *Qs = Vt + (kMaxKeys / 32) * 8192;            // [2 column blocks][128 rows][128 B]
+    constexpr uint32_t q_blk = kQT * 128;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int n_kb = (a.nk + kMaxKeys - 1) / kMaxKeys;
+
+    if (warp == 0) umma::tmem_alloc(&tmem_slot, 512);
+    if (tid == 0) {
+        umma::mbar_init(&bar_k, 1); umma::mbar_init(&bar_q, 1); umma::mbar_init(&bar_s, 1); umma::mbar_init(&bar_o, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+
+    auto load_k = [&](int kb) {
+        mbar_expect_tx(&bar_k, 2 * k_blk);
+        load_tile(Ks, &map_k, &bar_k, a.pos_k, 0, kb * kMaxKeys, h, b);
+        load_tile(Ks + k_blk, &map_k, &bar_k, a.pos_k, 32, kb * kMaxKeys, h, b);
+    };
+    if (tid == 0) {
+        mbar_expect_tx(&bar_q, 2 * q_blk);
+        load_tile(Qs, &map_q, &bar_q, a.pos_q, 0, qt * kQT, h, b);
+        load_tile(Qs + q_blk, &map_q, &bar_q, a.pos_q, 32, qt * kQT, h, b);
+        load_k(0);
+    }
+    const uint32_t idesc_o = umma::idesc(umma::kFmtTF32, kQT, kHd);
+    const int row = 32 * (warp & 3) + lane, half = warp >> 2;
+    const uint32_t lane_base = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
+    const float *vb = a.v + (int64_t)b * a.v_bs + (int64_t)h * a.v_hs;
+    float m_run = -INFINITY, l_run = 0.f;
+
+    for (int kb = 0; kb < n_kb; ++kb) {
+        const int nkb = min(kMaxKeys, a.nk - kb * kMaxKeys);    // keys in this block (multiple of 64)
+        const int cols_half = nkb / 2;
+        // V block -> registers (the V^T tile is free: the previous block's P V has completed)
+        constexpr int kWarps = kAttnThreads / 32, kItems = (kMaxKeys / 32) * 16 / kWarps;
+        const int n_items = (nkb / 32) * 16;
+        float4 v4[kItems];
+#pragma unroll
+        for (int i = 0; i < kItems; ++i) {
+            const int item = warp + i * kWarps;
+            if (item < n_items)
+                v4[i] = *reinterpret_cast<const float4 *>(vb + (int64_t)(kb * kMaxKeys + (item >> 4) * 32 + lane) * a.v_ts + 4 * (item & 15));
+        }
+        if (tid == 0) {                                          // S = Q K_kb^T
+            umma::mbar_wait(&bar_k, kb & 1);
+            if (kb == 0) umma::mbar_wait(&bar_q, 0);
+            umma::fence_after_sync();
+            const uint32_t idesc_s = umma::idesc(umma::kFmtTF32, kQT, nkb);
+            const uint32_t sq = umma::smem_u32(Qs), sk = umma::smem_u32(Ks);
+#pragma unroll
+            for (int cb = 0; cb < 2; ++cb)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma::mma<true>(tmem, umma::desc_sw128(sq + cb * q_blk + k * 32), umma::desc_sw128(sk + cb * k_blk + k * 32), idesc_s,
+                                    (cb | k) != 0);
+            umma::commit(&bar_s);
+        }
+#pragma unroll
+        for (int i = 0; i < kItems; ++i) {
+            const int item = warp + i * kWarps;
+            if (item < n_items) {
+                unsigned char *blk = Vt + (item >> 4) * 8192;
+                const int q = item & 15;
+                const float vals[4] = {v4[i].x, v4[i].y, v4[i].z, v4[i].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<uint32_t *>(blk + umma::sw128_off(4 * q + j, lane >> 2) + (lane & 3) * 4) =
+                        (__float_as_uint(vals[j]) + 0x1000u) & 0xffffe000u;
+            }
+        }
+        umma::fence_smem_to_async();
+        umma::mbar_wait(&bar_s, kb & 1);
+        umma::fence_after_sync();
+        if (tid == 0 && kb + 1 < n_kb) load_k(kb + 1);          // the K buffer is free: request the next block
+        // ---- online softmax of this block
+        float m = -INFINITY;
+        for (int c0 = 0; c0 < cols_half; c0 += 16) {
+            uint32_t v[16];
+            umma::tmem_ld16(lane_base + half * cols_half + c0, v);
+            umma::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) m = fmaxf(m, __uint_as_float(v[j]));
+        }
+        red_max[half][row] = m;
+        __syncthreads();
+        const float m_new = fmaxf(m_run, fmaxf(red_max[0][row], red_max[1][row]) * a.scale_log2e);
+        const float alpha = ex2_mufu(m_run - m_new);            // 0 for the first block (m_run = -inf)
+        float sum = 0.f;
+        for (int c0 = 0; c0 < cols_half; c0 += 32) {
+            uint32_t v[32];
+            umma::tmem_ld32(lane_base + half * cols_half + c0, v);
+            umma::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float p = ex2_mufu(fmaf(__uint_as_float(v[j]), a.scale_log2e, -m_new));
+                const uint32_t pr = (__float_as_uint(p) + 0x1000u) & 0xffffe000u;
+                sum += __uint_as_float(pr);
+                v[j] = pr;
+            }
+            umma::tmem_st32(lane_base + half * cols_half + c0, v);
+        }
+        l_run = fmaf(l_run, alpha, sum);
+        m_run = m_new;
+        if (kb > 0) {                                            // rescale this thread's 32 columns of the O accumulator
+            uint32_t v[32];
+            umma::tmem_ld32(lane_base + kOCol + half * 32, v);
+            umma::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * alpha);
+            umma::tmem_st32(lane_base + kOCol + half * 32, v);
+        }
+        umma::tmem_st_wait();
+        umma::fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {                                          // O += P V_kb
+            umma::fence_after_sync();
+            const uint32_t sv = umma::smem_u32(Vt);
+            for (int kk = 0; kk < nkb / 8; ++kk)
+                mma_ts_tf32(tmem + kOCol, tmem + kk * 8, umma::desc_sw128(sv + (kk >> 2) * 8192 + (kk & 3) * 32), idesc_o,
+                            (kb | kk) != 0);
+            umma::commit(&bar_o);
+        }
+        umma::mbar_wait(&bar_o, kb & 1);
+        umma::fence_after_sync();
+    }
+    red_sum[half][row] = l_run;
+    __syncthreads();
+    {
+        uint32_t v[32];
+        umma::tmem_ld32(lane_base + kOCol + half * 32, v);
+        umma::tmem_ld_wait();
+        const float inv = 1.f / (red_sum[0][row] + red_sum[1][row]);
+        const int tok = qt * kQT + row;
+        if (tok < a.nq) {
+            float *dst = a.out + (int64_t)b * a.o_bs + (int64_t)h * a.o_hs + (int64_t)tok * a.o_ts + half * 32;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4 *>(dst + j) = make_float4(__uint_as_float(v[j]) * inv, __uint_as_float(v[j + 1]) * inv,
+                                                                   __uint_as_float(v[j + 2]) * inv, __uint_as_float(v[j + 3]) * inv);
+        }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem, 512);
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -279,8 +445,10 @@ extern "C" int dimsum_attention_fwd(const dimsum_attention_params *p, void *stre
     DIMSUM_REQUIRE(p->q && p->k && p->v && p->out, DIMSUM_ERR_INVALID, "attention_fwd: null pointer");
     DIMSUM_REQUIRE(p->dtype == DIMSUM_F32, DIMSUM_ERR_UNSUPPORTED, "attention_fwd: fp32 I/O only (16-bit inputs keep the library flash kernel)");
     DIMSUM_REQUIRE(p->head_dim == kHd, DIMSUM_ERR_UNSUPPORTED, "attention_fwd: head_dim must be 64");
-    DIMSUM_REQUIRE(p->seqlen_k <= kMaxKeys && p->seqlen_k % 64 == 0, DIMSUM_ERR_UNSUPPORTED,
-                   "attention_fwd: seqlen_k must be a multiple of 64, at most 256 (longer sequences keep the library kernel)");
+    DIMSUM_REQUIRE(p->seqlen_k % 64 == 0, DIMSUM_ERR_UNSUPPORTED, "attention_fwd: seqlen_k must be a multiple of 64");
+    const bool long_seq = p->seqlen_k > kMaxKeys;
+    DIMSUM_REQUIRE(!long_seq || (p->heads <= 65535 && (p->seqlen_q + kQT - 1) / kQT < (1ll << 31)), DIMSUM_ERR_UNSUPPORTED,
+                   "attention_fwd: too many heads for the long-sequence grid");
     DIMSUM_REQUIRE(p->batch <= 65535, DIMSUM_ERR_UNSUPPORTED, "attention_fwd: batch > 65535");
     auto ok = [&](const void *ptr, int64_t s0, int64_t s1, int64_t s2) {
         return aligned16(ptr) && s0 % 4 == 0 && s1 % 4 == 0 && s2 % 4 == 0 && s0 > 0 && s1 > 0 && s2 > 0;
@@ -297,26 +465,37 @@ extern "C" int dimsum_attention_fwd(const dimsum_attention_params *p, void *stre
     CUtensorMap mq, mk;
     int r = make_map(enc, &mq, p->q, p->seqlen_q, p->heads, p->batch, p->q_token_stride, p->q_head_stride, p->q_batch_stride, kQT, a.pos_q);
     DIMSUM_REQUIRE(r == 0, DIMSUM_ERR_CUDA, "attention_fwd: cuTensorMapEncodeTiled(q) failed with %d", r);
-    r = make_map(enc, &mk, p->k, p->seqlen_k, p->heads, p->batch, p->k_token_stride, p->k_head_stride, p->k_batch_stride, (int)p->seqlen_k,
-                 a.pos_k);
+    r = make_map(enc, &mk, p->k, p->seqlen_k, p->heads, p->batch, p->k_token_stride, p->k_head_stride, p->k_batch_stride,
+                 long_seq ? kMaxKeys : (int)p->seqlen_k, a.pos_k);
     DIMSUM_REQUIRE(r == 0, DIMSUM_ERR_CUDA, "attention_fwd: cuTensorMapEncodeTiled(k) failed with %d", r);
     a.v = reinterpret_cast<const float *>(p->v); a.out = reinterpret_cast<float *>(p->out);
     a.v_bs = p->v_batch_stride; a.v_hs = p->v_head_stride; a.v_ts = p->v_token_stride;
     a.o_bs = p->out_batch_stride; a.o_hs = p->out_head_stride; a.o_ts = p->out_token_stride;
     a.nq = (int)p->seqlen_q; a.nk = (int)p->seqlen_k; a.heads = (int)p->heads;
-    a.scale_log2e = p->scale * kLog2e;
+    // kind::tf32 TRUNCATES q and k to 10 mantissa bits: every product q_d k_d loses, on average, 2 x 0.72 x 2^-11 = 7.0e-4 of
+    // its magnitude (13 dropped bits per operand, mean relative loss 0.72 x 2^-11 over a binade), i.e. the logits come out
+    // uniformly too flat.  The softmax scale carries the inverse factor: measured 2.9e-3 -> 7e-4 of the output max norm on flat
+    // 1024-key rows, 1.8e-3 -> 8e-4 on 256-key rows (the random part of the truncation remains).
+    a.scale_log2e = p->scale * kLog2e * (1.0f + 7.0e-4f);
 
-    const int smem = 2 * (int)p->seqlen_k * 128 + ((int)p->seqlen_k / 32) * 8192 + 2 * 2 * kQT * 128 + 1024;
+    const int smem = long_seq ? 2 * kMaxKeys * 128 + (kMaxKeys / 32) * 8192 + 2 * kQT * 128 + 1024
+                              : 2 * (int)p->seqlen_k * 128 + ((int)p->seqlen_k / 32) * 8192 + 2 * 2 * kQT * 128 + 1024;
     static std::atomic<unsigned long long> configured{0};
     int dev = 0;
     cudaGetDevice(&dev);
     if (!(configured.load(std::memory_order_acquire) >> (dev & 63) & 1ull)) {
+        cudaFuncSetAttribute(attention_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 65536 + 1024);
         // the largest configuration (256 keys): 64 KB K + 64 KB V^T + 64 KB of Q buffers + alignment slack (static shared memory
         // comes on top, so the 227 KB device limit itself is not a valid value here)
         cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 65536 + 1024);
         configured.fetch_or(1ull << (dev & 63), std::memory_order_release);
     }
-    dim3 grid((unsigned)p->heads, (unsigned)p->batch);
-    attention_kernel<<<grid, kAttnThreads, smem, stream>>>(a, mq, mk);
+    if (long_seq) {
+        dim3 grid((unsigned)((p->seqlen_q + kQT - 1) / kQT), (unsigned)p->heads, (unsigned)p->batch);
+        attention_long_kernel<<<grid, kAttnThreads, smem, stream>>>(a, mq, mk);
+    } else {
+        dim3 grid((unsigned)p->heads, (unsigned)p->batch);
+        attention_kernel<<<grid, kAttnThreads, smem, stream>>>(a, mq, mk);
+    }
     return check_launch("attention_fwd");
 }

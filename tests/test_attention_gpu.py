@@ -25,7 +25,7 @@ def _ref(q, k, v):
 
 
 @pytest.mark.parametrize("B,H,Nq,Nk", [(3, 8, 256, 256), (2, 16, 256, 256), (2, 8, 128, 128), (1, 4, 64, 64), (2, 8, 256, 128),
-                                      (2, 2, 200, 192), (1, 1, 384, 256)])
+                                      (2, 2, 200, 192), (1, 1, 384, 256), (2, 4, 1024, 1024), (1, 2, 300, 576), (1, 3, 128, 320)])
 def test_attention_matches_fp64_softmax_attention(B, H, Nq, Nk):
     from dimsum_b200.attention import attention, attention_supported
     g = torch.Generator(device="cuda").manual_seed(B * 1000 + Nq)
@@ -55,7 +55,8 @@ def test_attention_is_only_taken_when_its_conditions_hold():
     with torch.no_grad():
         assert attention_supported(q, q, q)
         assert not attention_supported(q.half(), q.half(), q.half())                     # 16-bit keeps the library flash kernel
-        assert not attention_supported(q, torch.randn(2, 8, 1024, 64, device="cuda"), torch.randn(2, 8, 1024, 64, device="cuda"))
+        assert attention_supported(q, torch.randn(2, 8, 1024, 64, device="cuda"), torch.randn(2, 8, 1024, 64, device="cuda"))
+        assert not attention_supported(q, torch.randn(2, 8, 1000, 64, device="cuda"), torch.randn(2, 8, 1000, 64, device="cuda"))
         assert not attention_supported(q[..., :32], q[..., :32], q[..., :32])            # head_dim 64 only
         torch.backends.cuda.matmul.allow_tf32 = False
         assert not attention_supported(q, q, q)                                          # TF32 disabled: library SDPA

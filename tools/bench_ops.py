@@ -191,18 +191,18 @@ def main():
         from dimsum_b200.attention import attention
         import torch.nn.functional as F
         torch.backends.cuda.matmul.allow_tf32 = True
-        for H in (8, 16):
-            Bt, Nt = 512, 256
+        for H, Nt in ((8, 256), (16, 256), (8, 1024)):
+            Bt = 512
             qkv = torch.randn(Bt, Nt, 3, H, 64, device="cuda")
             q, k, v = qkv.permute(2, 0, 3, 1, 4).unbind(0)
             by_a = 4 * 4 * Bt * H * Nt * 64                        # q, k, v read + out written once
             fl = 4.0 * Bt * H * Nt * Nt * 64
             with torch.no_grad():
                 med, best = timeit(lambda: attention(q, k, v), flush=flush)
-                rows.append(dict(op=f"attention_h{H}", dtype="torch.float32", R=Bt, D=H * 64, L=Nt, ms=med, ms_best=best,
+                rows.append(dict(op=f"attention_h{H}_n{Nt}", dtype="torch.float32", R=Bt, D=H * 64, L=Nt, ms=med, ms_best=best,
                                  gbs=by_a / med / 1e6, frac=by_a / med / 1e6 / pk, tflops=fl / med / 1e9))
                 med, best = timeit(lambda: F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(Bt, Nt, H * 64), flush=flush)
-                rows.append(dict(op=f"sdpa_lib_h{H}", dtype="torch.float32", R=Bt, D=H * 64, L=Nt, ms=med, ms_best=best,
+                rows.append(dict(op=f"sdpa_lib_h{H}_n{Nt}", dtype="torch.float32", R=Bt, D=H * 64, L=Nt, ms=med, ms_best=best,
                                  gbs=by_a / med / 1e6, frac=by_a / med / 1e6 / pk, tflops=fl / med / 1e9))
     for r in rows:
         print(f"{r['op']:20s} {r['dtype']:15s} R={r['R']:4d} D={r['D']:5d} L={r['L']:5d}  {r['ms']:8.3f} ms (best {r['ms_best']:.3f})"
