@@ -3,8 +3,8 @@
 Reference call sites: `F.scaled_dot_product_attention(q, k, v)` in dimsum/attention_fusion.py:61-84 and the timm `Attention`
 of the shared DiTBlock (dimsum/models_dim.py:1532-1554).  fp32 tensors, TF32 tensor-core products with fp32 accumulation and
 an fp32 softmax -- the precision class cuBLAS uses for the surrounding GEMMs when `torch.backends.cuda.matmul.allow_tf32` is
-on, which is the condition for taking this path.  Up to 256 keys one CTA per (batch, head) keeps K and V^T on chip for both query
-tiles; longer sequences (512px: 1024 tokens) walk the keys in blocks of 256 with the online softmax.  Forward only: recorded
+on, which is the condition for taking this path.  One CTA per (batch, head, 128-query tile) walks the keys in blocks of 128
+with the online softmax, two CTAs per SM (256 tokens at 256px, 1024 at 512px).  Forward only: recorded
 (training) passes and 16-bit autocast keep the library SDPA (a library GPU kernel, not a fallback of this repo's hot path).
 """
 import os

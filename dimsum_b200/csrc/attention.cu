@@ -6,21 +6,25 @@
 // fp32 sampling step the library kernel PyTorch picks for fp32 (`fmha_cutlassF_f32_aligned_64x64_rf_sm80`, an Ampere
 // kernel) was 24 % of the device time.
 //
-// Up to 256 keys: one CTA per (batch, head).  K (all <= 256 keys, two 128-byte column blocks of head_dim) and the query tiles arrive by TMA
-// in the tensor core's SWIZZLE_128B K-major layout; V is transposed on the way in (V^T is the K-major B operand of P V;
-// kind::tf32 has no MN-major mode) with conflict-free 4-byte stores.  Per 128-query tile:
-//   S = Q K^T      8 tcgen05.mma (M 128, N = keys, K 8) into TMEM columns [0, keys)
-//   softmax        8 warps: thread = (row, half of the keys); tcgen05.ld, row max / sum exchanged through shared memory,
-//                  p = 2^((s - max) scale log2 e) written back IN PLACE with tcgen05.st (P never touches shared memory)
-//   O = P V        keys / 8 tcgen05.mma with the A operand read from TMEM, into TMEM columns [256, 320)
-//   epilogue       tcgen05.ld, times 1 / row sum, 128-byte contiguous stores straight into the (batch, tokens, heads x 64)
-//                  layout the output projection reads (no transpose / cat copies).
-// The second query tile of a 256-token row reuses K and V^T; its Q tile is prefetched while the first is in flight.
-// TF32 (10-bit mantissa, fp32 accumulate) is what cuBLAS uses for the surrounding GEMMs under allow_tf32; callers that
-// disable TF32 keep the library SDPA.
+// One CTA per (batch, head, 128-query tile), two CTAs per SM.  The query tile and the key blocks (128 keys) arrive by 4-D TMA
+// tensor maps in the tensor core's SWIZZLE_128B K-major layout (two 128-byte column blocks of head_dim); V blocks are transposed
+// on the way in (V^T is the K-major B operand of P V; kind::tf32 has no MN-major mode) with conflict-free 4-byte stores, rounded to
+// nearest tf32.  Per key block:
+//   S = Q K^T      8 tcgen05.mma (M 128, N = keys of the block, K 8) into TMEM columns [0, 128)
+//   softmax        8 warps: thread = (row, half of the block's keys); tcgen05.ld, block max exchanged through shared memory, online
+//                  update of the running max / sum, p = 2^((s - max) scale log2 e) rounded to nearest tf32 and written back IN
+//                  PLACE with tcgen05.st (P never touches shared memory); O (TMEM) rescaled when a later block raises the max
+//   O += P V       keys / 8 tcgen05.mma with the A operand read from TMEM, into TMEM columns [128, 192)
+// and at the end: tcgen05.ld, times 1 / row sum, 128-byte contiguous stores straight into the (batch, tokens, heads x 64) layout the
+// output projection reads (no transpose / cat copies).  The next K block is requested as soon as this block's S exists; with 96 KB
+// of shared memory and 256 TMEM columns per CTA two CTAs share an SM and fill each other's load / softmax / MMA phases (measured:
+// 0.48 ms vs 0.55 ms for a resident-K one-CTA-per-SM variant at 256 tokens, 5.3 vs 6.8 ms with 256-key blocks at 1024 tokens).
+// TF32 (10-bit mantissa, fp32 accumulate) is what cuBLAS uses for the surrounding GEMMs under allow_tf32; callers that disable
+// TF32 keep the library SDPA.
 #include <cuda.h>
 
 #include <atomic>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "umma.cuh"
@@ -30,9 +34,7 @@ namespace {
 
 constexpr int kHd = 64;            // head dim
 constexpr int kQT = 128;           // queries per tile == MMA M
-constexpr int kMaxKeys = 256;
 constexpr int kAttnThreads = 256;
-constexpr int kOCol = 256;         // TMEM column of the O accumulator (S / P occupy [0, keys))
 
 struct AttnArgs {
     const float *v;
@@ -63,198 +65,31 @@ DEV void load_tile(void *dst, const CUtensorMap *map, uint64_t *bar, const int (
     tma_load_4d(dst, map, bar, d0, c[0], c[1], c[2]);
 }
 
-__global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const AttnArgs a, const __grid_constant__ CUtensorMap map_q,
-                                                                    const __grid_constant__ CUtensorMap map_k) {
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    __shared__ uint64_t bar_k, bar_q[2], bar_s, bar_o;
-    __shared__ uint32_t tmem_slot;
-    __shared__ float red_max[2][kQT], red_sum[2][kQT];
-    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int nk = a.nk;
-    const uint32_t k_blk = (uint32_t)nk * 128;                  // bytes of one 128-byte-wide column block of K (nk rows)
-    unsigned char *Ks = smem;                                   // [2 column blocks of head_dim][nk rows][128 B]
-    unsigned char *Vt = Ks + 2 * k_blk;                         // [nk / 32 column blocks of keys][64 rows (head_dim)][128 B]
-    unsigned char *Qs = Vt + (uint32_t)(nk / 32) * 8192;        // [2 buffers][2 column blocks][128 rows][128 B]
-    constexpr uint32_t q_blk = kQT * 128, q_buf = 2 * q_blk;
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int h = blockIdx.x, b = blockIdx.y;
-    const int n_qt = (a.nq + kQT - 1) / kQT;
-
-    if (warp == 0) umma::tmem_alloc(&tmem_slot, 512);
-    if (tid == 0) {
-        umma::mbar_init(&bar_k, 1); umma::mbar_init(&bar_q[0], 1); umma::mbar_init(&bar_q[1], 1);
-        umma::mbar_init(&bar_s, 1); umma::mbar_init(&bar_o, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    umma::fence_before_sync();
-    __syncthreads();
-    umma::fence_after_sync();
-    const uint32_t tmem = tmem_slot;
-
-    if (tid == 0) {                                             // K (both column blocks) and the first two query tiles
-        mbar_expect_tx(&bar_k, 2 * k_blk);
-        load_tile(Ks, &map_k, &bar_k, a.pos_k, 0, 0, h, b);
-        load_tile(Ks + k_blk, &map_k, &bar_k, a.pos_k, 32, 0, h, b);
-        for (int t = 0; t < 2 && t < n_qt; ++t) {
-            mbar_expect_tx(&bar_q[t], q_buf);
-            load_tile(Qs + t * q_buf, &map_q, &bar_q[t], a.pos_q, 0, t * kQT, h, b);
-            load_tile(Qs + t * q_buf + q_blk, &map_q, &bar_q[t], a.pos_q, 32, t * kQT, h, b);
-        }
-    }
-    const uint32_t idesc_s = umma::idesc(umma::kFmtTF32, kQT, nk);
-    const uint32_t idesc_o = umma::idesc(umma::kFmtTF32, kQT, kHd);
-    // S = Q K^T of query tile `qt` (one thread): 2 column blocks of head_dim x 4 K steps
-    auto issue_s = [&](int qt) {
-        const int buf = qt & 1;
-        umma::mbar_wait(&bar_q[buf], (qt >> 1) & 1);
-        umma::fence_after_sync();
-        const uint32_t sq = umma::smem_u32(Qs + buf * q_buf), sk = umma::smem_u32(Ks);
-#pragma unroll
-        for (int cb = 0; cb < 2; ++cb)
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                umma::mma<true>(tmem, umma::desc_sw128(sq + cb * q_blk + k * 32), umma::desc_sw128(sk + cb * k_blk + k * 32), idesc_s,
-                                (cb | k) != 0);
-        umma::commit(&bar_s);
-    };
-    // V^T: lane = key inside a 32-key column block, item = (column block, quad of head_dim); 4-byte stores of a warp fall in
-    // 32 distinct banks (one 128-byte row, swizzled chunk = lane / 4)
-    {
-        const float *vb = a.v + (int64_t)b * a.v_bs + (int64_t)h * a.v_hs;
-        constexpr int kWarps = kAttnThreads / 32, kItems = (kMaxKeys / 32) * 16 / kWarps;      // <= 16 items per warp
-        const int n_items = (nk / 32) * 16;
-        float4 v4[kItems];
-#pragma unroll
-        for (int i = 0; i < kItems; ++i) {                       // all loads in flight before the first store
-            const int item = warp + i * kWarps;
-            if (item < n_items)
-                v4[i] = *reinterpret_cast<const float4 *>(vb + (int64_t)((item >> 4) * 32 + lane) * a.v_ts + 4 * (item & 15));
-        }
-        if (tid == 0) {                                           // the tensor core starts on tile 0 while V^T is being stored
-            umma::mbar_wait(&bar_k, 0);
-            issue_s(0);
-        }
-#pragma unroll
-        for (int i = 0; i < kItems; ++i) {
-            const int item = warp + i * kWarps;
-            if (item < n_items) {
-                unsigned char *blk = Vt + (item >> 4) * 8192;
-                const int q = item & 15;
-                const float vals[4] = {v4[i].x, v4[i].y, v4[i].z, v4[i].w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j)              // rounded to nearest tf32 on the way (the tensor core would truncate)
-                    *reinterpret_cast<uint32_t *>(blk + umma::sw128_off(4 * q + j, lane >> 2) + (lane & 3) * 4) =
-                        (__float_as_uint(vals[j]) + 0x1000u) & 0xffffe000u;
-            }
-        }
-    }
-    umma::fence_smem_to_async();
-    __syncthreads();
-
-    const int row = 32 * (warp & 3) + lane, half = warp >> 2;      // this thread's accumulator row and half of the columns
-    const uint32_t lane_base = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
-    const int cols_half = nk / 2;                                   // S columns per half (multiple of 32)
-
-    for (int qt = 0; qt < n_qt; ++qt) {
-        const int buf = qt & 1;
-        umma::mbar_wait(&bar_s, qt & 1);
-        umma::fence_after_sync();
-        if (tid == 0 && qt + 2 < n_qt) {                            // the Q buffer is free again: prefetch the tile after next
-            mbar_expect_tx(&bar_q[buf], q_buf);
-            load_tile(Qs + buf * q_buf, &map_q, &bar_q[buf], a.pos_q, 0, (qt + 2) * kQT, h, b);
-            load_tile(Qs + buf * q_buf + q_blk, &map_q, &bar_q[buf], a.pos_q, 32, (qt + 2) * kQT, h, b);
-        }
-        // ---- softmax over this thread's half of row `row`
-        float m = -INFINITY;
-        for (int c0 = 0; c0 < cols_half; c0 += 16) {
-            uint32_t v[16];
-            umma::tmem_ld16(lane_base + half * cols_half + c0, v);
-            umma::tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 16; ++j) m = fmaxf(m, __uint_as_float(v[j]));
-        }
-        red_max[half][row] = m;
-        __syncthreads();
-        m = fmaxf(red_max[0][row], red_max[1][row]) * a.scale_log2e;
-        float sum = 0.f;
-        for (int c0 = 0; c0 < cols_half; c0 += 32) {
-            uint32_t v[32];
-            umma::tmem_ld32(lane_base + half * cols_half + c0, v);
-            umma::tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                // the tensor core TRUNCATES fp32 operands to tf32, which would bias every probability low (2.4e-3 on the output
-                // against 5e-4 with rounding): round to nearest here, and normalise by the sum of the ROUNDED values
-                const float p = ex2_mufu(fmaf(__uint_as_float(v[j]), a.scale_log2e, -m));
-                const uint32_t pr = (__float_as_uint(p) + 0x1000u) & 0xffffe000u;
-                sum += __uint_as_float(pr);
-                v[j] = pr;
-            }
-            umma::tmem_st32(lane_base + half * cols_half + c0, v);
-        }
-        umma::tmem_st_wait();
-        red_sum[half][row] = sum;
-        umma::fence_before_sync();
-        __syncthreads();
-        // ---- O = P V: A from TMEM (P, columns [0, nk)), B = V^T from shared memory
-        if (tid == 0) {
-            umma::fence_after_sync();
-            const uint32_t sv = umma::smem_u32(Vt);
-            for (int kk = 0; kk < nk / 8; ++kk)
-                mma_ts_tf32(tmem + kOCol, tmem + kk * 8, umma::desc_sw128(sv + (kk >> 2) * 8192 + (kk & 3) * 32), idesc_o, kk != 0);
-            umma::commit(&bar_o);
-        }
-        umma::mbar_wait(&bar_o, qt & 1);
-        umma::fence_after_sync();
-        if (tid == 0 && qt + 1 < n_qt) issue_s(qt + 1);            // P has been consumed: the next tile's S overlaps this epilogue
-        // ---- epilogue: thread = (row, 32 of the 64 output columns)
-        {
-            uint32_t v[32];
-            umma::tmem_ld32(lane_base + kOCol + half * 32, v);
-            umma::tmem_ld_wait();
-            const float inv = 1.f / (red_sum[0][row] + red_sum[1][row]);
-            const int tok = qt * kQT + row;
-            if (tok < a.nq) {
-                float *dst = a.out + (int64_t)b * a.o_bs + (int64_t)h * a.o_hs + (int64_t)tok * a.o_ts + half * 32;
-#pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<float4 *>(dst + j) = make_float4(__uint_as_float(v[j]) * inv, __uint_as_float(v[j + 1]) * inv,
-                                                                       __uint_as_float(v[j + 2]) * inv, __uint_as_float(v[j + 3]) * inv);
-            }
-        }
-        // no barrier here: the next tile's softmax synchronises the CTA before anything of this tile is overwritten
-        // (red_sum is rewritten after its __syncthreads, the O columns by an MMA issued after its second one)
-    }
-    umma::fence_before_sync();
-    __syncthreads();
-    if (warp == 0) umma::tmem_dealloc(tmem, 512);
-}
-
-
-// ---- sequences beyond 256 keys (512px configuration: 1024 tokens) -------------------------------------------------------------
-// One CTA per (batch, head, 128-query tile); the keys are walked in blocks of up to 256 with the online softmax: running row max
-// m and row sum l per thread, p = 2^(s c - m_new), l = l 2^(m - m_new) + sum p, and the O accumulator (TMEM) rescaled by
-// 2^(m - m_new) with tcgen05.ld / st before the block's P V is accumulated on top.  K blocks arrive by TMA (the next one is
-// requested as soon as this block's S = Q K^T has been computed), V blocks are transposed on the way in as above.
-__global__ void __launch_bounds__(kAttnThreads, 1) attention_long_kernel(const AttnArgs a, const __grid_constant__ CUtensorMap map_q,
-                                                                         const __grid_constant__ CUtensorMap map_k) {
+// One CTA per (batch, head, 128-query tile); the keys are walked in blocks of KB with the online softmax: running row max m and
+// row sum l per thread, p = 2^(s c - m_new), l = l 2^(m - m_new) + sum p, and the O accumulator (TMEM) rescaled by 2^(m - m_new)
+// with tcgen05.ld / st before the block's P V is accumulated on top.  K blocks arrive by TMA (the next one is requested as soon
+// as this block's S = Q K^T has been computed), V blocks are transposed on the way in.
+template <int KB>                         // keys per block: 128 (two CTAs per SM overlap each other's phases; the default) or 256
+__global__ void __launch_bounds__(kAttnThreads, KB == 128 ? 2 : 1) attention_kernel(const AttnArgs a,
+                                                                                        const __grid_constant__ CUtensorMap map_q,
+                                                                                        const __grid_constant__ CUtensorMap map_k) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ uint64_t bar_k, bar_q, bar_s, bar_o;
     __shared__ uint32_t tmem_slot;
     __shared__ float red_max[2][kQT], red_sum[2][kQT];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    constexpr uint32_t k_blk = kMaxKeys * 128;                  // one column block of a 256-key K block
+    constexpr uint32_t k_blk = KB * 128;                        // one column block of a KB-key K block
     unsigned char *Ks = smem;                                   // [2 column blocks of head_dim][256 rows][128 B]
     unsigned char *Vt = Ks + 2 * k_blk;                         // [8 column blocks of 32 keys][64 rows][128 B]
-    unsigned char *Qs = Vt + (kMaxKeys / 32) * 8192;            // [2 column blocks][128 rows][128 B]
+    unsigned char *Qs = Vt + (KB / 32) * 8192;                  // [2 column blocks][128 rows][128 B]
     constexpr uint32_t q_blk = kQT * 128;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-    const int n_kb = (a.nk + kMaxKeys - 1) / kMaxKeys;
+    const int n_kb = (a.nk + KB - 1) / KB;
+    constexpr uint32_t kTmemCols = KB == 128 ? 256 : 512, kOColL = KB;   // S / P in [0, KB), O in [KB, KB + 64)
 
-    if (warp == 0) umma::tmem_alloc(&tmem_slot, 512);
+    if (warp == 0) umma::tmem_alloc(&tmem_slot, kTmemCols);
     if (tid == 0) {
         umma::mbar_init(&bar_k, 1); umma::mbar_init(&bar_q, 1); umma::mbar_init(&bar_s, 1); umma::mbar_init(&bar_o, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -266,8 +101,8 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_long_kernel(const A
 
     auto load_k = [&](int kb) {
         mbar_expect_tx(&bar_k, 2 * k_blk);
-        load_tile(Ks, &map_k, &bar_k, a.pos_k, 0, kb * kMaxKeys, h, b);
-        load_tile(Ks + k_blk, &map_k, &bar_k, a.pos_k, 32, kb * kMaxKeys, h, b);
+        load_tile(Ks, &map_k, &bar_k, a.pos_k, 0, kb * KB, h, b);
+        load_tile(Ks + k_blk, &map_k, &bar_k, a.pos_k, 32, kb * KB, h, b);
     };
     if (tid == 0) {
         mbar_expect_tx(&bar_q, 2 * q_blk);
@@ -282,17 +117,17 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_long_kernel(const A
     float m_run = -INFINITY, l_run = 0.f;
 
     for (int kb = 0; kb < n_kb; ++kb) {
-        const int nkb = min(kMaxKeys, a.nk - kb * kMaxKeys);    // keys in this block (multiple of 64)
+        const int nkb = min(KB, a.nk - kb * KB);                // keys in this block (multiple of 64)
         const int cols_half = nkb / 2;
         // V block -> registers (the V^T tile is free: the previous block's P V has completed)
-        constexpr int kWarps = kAttnThreads / 32, kItems = (kMaxKeys / 32) * 16 / kWarps;
+        constexpr int kWarps = kAttnThreads / 32, kItems = (KB / 32) * 16 / kWarps;
         const int n_items = (nkb / 32) * 16;
         float4 v4[kItems];
 #pragma unroll
         for (int i = 0; i < kItems; ++i) {
             const int item = warp + i * kWarps;
             if (item < n_items)
-                v4[i] = *reinterpret_cast<const float4 *>(vb + (int64_t)(kb * kMaxKeys + (item >> 4) * 32 + lane) * a.v_ts + 4 * (item & 15));
+                v4[i] = *reinterpret_cast<const float4 *>(vb + (int64_t)(kb * KB + (item >> 4) * 32 + lane) * a.v_ts + 4 * (item & 15));
         }
         if (tid == 0) {                                          // S = Q K_kb^T
             umma::mbar_wait(&bar_k, kb & 1);
@@ -356,11 +191,11 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_long_kernel(const A
         m_run = m_new;
         if (kb > 0) {                                            // rescale this thread's 32 columns of the O accumulator
             uint32_t v[32];
-            umma::tmem_ld32(lane_base + kOCol + half * 32, v);
+            umma::tmem_ld32(lane_base + kOColL + half * 32, v);
             umma::tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * alpha);
-            umma::tmem_st32(lane_base + kOCol + half * 32, v);
+            umma::tmem_st32(lane_base + kOColL + half * 32, v);
         }
         umma::tmem_st_wait();
         umma::fence_before_sync();
@@ -369,7 +204,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_long_kernel(const A
             umma::fence_after_sync();
             const uint32_t sv = umma::smem_u32(Vt);
             for (int kk = 0; kk < nkb / 8; ++kk)
-                mma_ts_tf32(tmem + kOCol, tmem + kk * 8, umma::desc_sw128(sv + (kk >> 2) * 8192 + (kk & 3) * 32), idesc_o,
+                mma_ts_tf32(tmem + kOColL, tmem + kk * 8, umma::desc_sw128(sv + (kk >> 2) * 8192 + (kk & 3) * 32), idesc_o,
                             (kb | kk) != 0);
             umma::commit(&bar_o);
         }
@@ -380,7 +215,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_long_kernel(const A
     __syncthreads();
     {
         uint32_t v[32];
-        umma::tmem_ld32(lane_base + kOCol + half * 32, v);
+        umma::tmem_ld32(lane_base + kOColL + half * 32, v);
         umma::tmem_ld_wait();
         const float inv = 1.f / (red_sum[0][row] + red_sum[1][row]);
         const int tok = qt * kQT + row;
@@ -394,7 +229,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_long_kernel(const A
     }
     umma::fence_before_sync();
     __syncthreads();
-    if (warp == 0) umma::tmem_dealloc(tmem, 512);
+    if (warp == 0) umma::tmem_dealloc(tmem, kTmemCols);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -446,9 +281,9 @@ extern "C" int dimsum_attention_fwd(const dimsum_attention_params *p, void *stre
     DIMSUM_REQUIRE(p->dtype == DIMSUM_F32, DIMSUM_ERR_UNSUPPORTED, "attention_fwd: fp32 I/O only (16-bit inputs keep the library flash kernel)");
     DIMSUM_REQUIRE(p->head_dim == kHd, DIMSUM_ERR_UNSUPPORTED, "attention_fwd: head_dim must be 64");
     DIMSUM_REQUIRE(p->seqlen_k % 64 == 0, DIMSUM_ERR_UNSUPPORTED, "attention_fwd: seqlen_k must be a multiple of 64");
-    const bool long_seq = p->seqlen_k > kMaxKeys;
-    DIMSUM_REQUIRE(!long_seq || (p->heads <= 65535 && (p->seqlen_q + kQT - 1) / kQT < (1ll << 31)), DIMSUM_ERR_UNSUPPORTED,
-                   "attention_fwd: too many heads for the long-sequence grid");
+    static const int block_env = [] { const char *e = getenv("DIMSUM_ATTN_BLOCK"); return e ? atoi(e) : 0; }();
+    const int kb_size = block_env == 256 ? 256 : 128;          // DIMSUM_ATTN_BLOCK=256: 256-key blocks, one CTA per SM (A/B runs)
+    DIMSUM_REQUIRE(p->heads <= 65535, DIMSUM_ERR_UNSUPPORTED, "attention_fwd: more than 65535 heads");
     DIMSUM_REQUIRE(p->batch <= 65535, DIMSUM_ERR_UNSUPPORTED, "attention_fwd: batch > 65535");
     auto ok = [&](const void *ptr, int64_t s0, int64_t s1, int64_t s2) {
         return aligned16(ptr) && s0 % 4 == 0 && s1 % 4 == 0 && s2 % 4 == 0 && s0 > 0 && s1 > 0 && s2 > 0;
@@ -466,7 +301,7 @@ extern "C" int dimsum_attention_fwd(const dimsum_attention_params *p, void *stre
     int r = make_map(enc, &mq, p->q, p->seqlen_q, p->heads, p->batch, p->q_token_stride, p->q_head_stride, p->q_batch_stride, kQT, a.pos_q);
     DIMSUM_REQUIRE(r == 0, DIMSUM_ERR_CUDA, "attention_fwd: cuTensorMapEncodeTiled(q) failed with %d", r);
     r = make_map(enc, &mk, p->k, p->seqlen_k, p->heads, p->batch, p->k_token_stride, p->k_head_stride, p->k_batch_stride,
-                 long_seq ? kMaxKeys : (int)p->seqlen_k, a.pos_k);
+                 kb_size, a.pos_k);
     DIMSUM_REQUIRE(r == 0, DIMSUM_ERR_CUDA, "attention_fwd: cuTensorMapEncodeTiled(k) failed with %d", r);
     a.v = reinterpret_cast<const float *>(p->v); a.out = reinterpret_cast<float *>(p->out);
     a.v_bs = p->v_batch_stride; a.v_hs = p->v_head_stride; a.v_ts = p->v_token_stride;
@@ -478,24 +313,17 @@ extern "C" int dimsum_attention_fwd(const dimsum_attention_params *p, void *stre
     // 1024-key rows, 1.8e-3 -> 8e-4 on 256-key rows (the random part of the truncation remains).
     a.scale_log2e = p->scale * kLog2e * (1.0f + 7.0e-4f);
 
-    const int smem = long_seq ? 2 * kMaxKeys * 128 + (kMaxKeys / 32) * 8192 + 2 * kQT * 128 + 1024
-                              : 2 * (int)p->seqlen_k * 128 + ((int)p->seqlen_k / 32) * 8192 + 2 * 2 * kQT * 128 + 1024;
+    const int smem = 2 * kb_size * 128 + (kb_size / 32) * 8192 + 2 * kQT * 128 + 1024;
     static std::atomic<unsigned long long> configured{0};
     int dev = 0;
     cudaGetDevice(&dev);
     if (!(configured.load(std::memory_order_acquire) >> (dev & 63) & 1ull)) {
-        cudaFuncSetAttribute(attention_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 65536 + 1024);
-        // the largest configuration (256 keys): 64 KB K + 64 KB V^T + 64 KB of Q buffers + alignment slack (static shared memory
-        // comes on top, so the 227 KB device limit itself is not a valid value here)
-        cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 65536 + 1024);
+        cudaFuncSetAttribute(attention_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 65536 + 1024);
+        cudaFuncSetAttribute(attention_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 32768 + 1024);
         configured.fetch_or(1ull << (dev & 63), std::memory_order_release);
     }
-    if (long_seq) {
-        dim3 grid((unsigned)((p->seqlen_q + kQT - 1) / kQT), (unsigned)p->heads, (unsigned)p->batch);
-        attention_long_kernel<<<grid, kAttnThreads, smem, stream>>>(a, mq, mk);
-    } else {
-        dim3 grid((unsigned)p->heads, (unsigned)p->batch);
-        attention_kernel<<<grid, kAttnThreads, smem, stream>>>(a, mq, mk);
-    }
+    dim3 grid((unsigned)((p->seqlen_q + kQT - 1) / kQT), (unsigned)p->heads, (unsigned)p->batch);
+    if (kb_size == 256) attention_kernel<256><<<grid, kAttnThreads, smem, stream>>>(a, mq, mk);
+    else attention_kernel<128><<<grid, kAttnThreads, smem, stream>>>(a, mq, mk);
     return check_launch("attention_fwd");
 }

@@ -196,8 +196,8 @@ int dimsum_conv_xproj_fwd(const dimsum_conv_xproj_params *p, void *stream);
  * the 256px configuration.  q, k, v: (batch, heads, seqlen, 64) views with innermost stride 1 and arbitrary positive,
  * 16-byte aligned batch / head / token strides (the slices of a fused qkv projection are taken in place); out: written as
  * out[b, h, token, :] with its own strides -- pass the strides of a (batch, tokens, heads * 64) buffer to get the layout the
- * output projection reads.  No mask, no dropout (the model uses neither).  head_dim == 64, seqlen_k % 64 == 0; up to 256 keys
- * stay on chip, longer sequences (512px: 1024 tokens) use the online softmax over key blocks of 256.
+ * output projection reads.  No mask, no dropout (the model uses neither).  head_dim == 64, seqlen_k % 64 == 0 (online softmax
+ * over key blocks of 128: any length, 256 tokens at 256px and 1024 at 512px).
  */
 typedef struct {
     int64_t batch, heads, seqlen_q, seqlen_k, head_dim, dtype;
