@@ -17,30 +17,38 @@
 //     accumulate in registers and meet the other 15 groups of the CTA once per 4 steps through shared memory;
 //   * what has to cross lanes per step is only the two 16-state dot products (sum_n e A, sum_n g B): 8 packed values per
 //     lane and 4 steps go through a padded transposing tile, lane j ends up with total j.
-// A CTA owns 64 rows and walks the sequence backwards in 16-step chunks restarted from the forward's 16-step
+// A CTA owns 32 rows (64 threads; 64 rows / 128 threads in the round-1 shape) and walks the sequence backwards in 16-step chunks restarted from the forward's 16-step
 // checkpoints (x): one forward sweep parks the state every 4 steps, then the four 4-step mini-chunks are replayed
 // (h and a history in registers) and swept in reverse.  Global memory sees ONE fp32 atomic per (l, n) per 64 rows, and
 // u / delta / dout / z / out / du / ddelta / dz move as coalesced 16-byte vectors.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace dimsum {
 namespace {
 
-constexpr int kT = 128;                    // threads per CTA
+// threads per CTA: 64 (32 rows; 7 CTAs = 14 warps per SM at 144 registers; the default) or 128 (64 rows; 3 CTAs = 12 warps per
+// SM at 168 registers, round 1)
 constexpr int kLn = 8;                     // lanes per row group (2 states each)
-constexpr int kGroups = kT / kLn;          // 16 row groups
-constexpr int kPairs = 2 * kGroups;        // 32 row pairs = 64 rows per CTA
-constexpr int kRowsB = 2 * kPairs;
+template <int KT> struct Cta {
+    static constexpr int kT = KT;
+    static constexpr int kGroups = KT / kLn;       // 16 (8) row groups
+    static constexpr int kPairs = 2 * kGroups;     // 32 (16) row pairs = 64 (32) rows per CTA
+    static constexpr int kRowsB = 2 * kPairs;
+    static constexpr int kMinCtas = KT == 128 ? 3 : 7;
+};
 constexpr int kSub = 16;                   // steps per chunk (== checkpoint spacing of the forward)
 constexpr int kMini = 4;                   // steps whose history lives in registers
 constexpr int kMinis = kSub / kMini;
 constexpr int kTileG = 2 * kMini + 1;      // float4 units per row group inside a slab (2 row pairs x 4 steps + 1: neighbouring
                                            // groups start 4 banks apart, so their 8-byte broadcast loads do not collide)
-constexpr int kTileM = kGroups * kTileG + 1;   // float4 units per mini-chunk slab of a [mini][row pair][step] tile; slab
-                                           // stride = 1 mod 8 makes the 16-byte stores of the prep pass conflict-free
+// float4 units per mini-chunk slab of a [mini][row pair][step] tile; slab stride = 1 mod 8 makes the 16-byte stores of the prep
+// pass conflict-free
+template <int KT> __device__ __host__ constexpr int tile_m() { return Cta<KT>::kGroups * kTileG + 1; }
 // element (mini m, row pair p, step i) of a row-pair tile
-__device__ __forceinline__ constexpr int tile_at(int m, int p, int i) { return m * kTileM + (p >> 1) * kTileG + (p & 1) * kMini + i; }
-constexpr int kMinCtas = 3;                 // CTAs per SM the register budget is cut for (168 registers; 128 spills)
+template <int KT>
+__device__ __forceinline__ constexpr int tile_at(int m, int p, int i) { return m * tile_m<KT>() + (p >> 1) * kTileG + (p & 1) * kMini + i; }
 constexpr int kStLane = 20;                // words per lane record of the transposing tile (8 packed values + pad)
 constexpr int kStGroup = kLn * kStLane + 16;   // words per group: odd multiple of 16 -> the two groups of a half warp use disjoint banks
 
@@ -55,23 +63,26 @@ struct ScanBwdArgs {
     int dim, seqlen, dstate, n_groups, n_chunks, softplus, vec_io, vec_bc;
 };
 
+template <int KT>
 struct BwdSmem {
-    // row-pair tiles, element (mini m, row pair p, step i) at [tile_at(m, p, i)]
-    float4 X[kMinis * kTileM];            // (delta r0, delta r1, delta*u r0, delta*u r1); later (ddelta r0, r1, du r0, r1)
-    float4 Y[kMinis * kTileM];            // (dy r0, dy r1, D dy r0, D dy r1)
-    float4 Z[kMinis * kTileM];            // (ln2 s' r0, ln2 s' r1, u s' r0, u s' r1) with s' = d softplus / d raw delta
+    static constexpr int kPairs = Cta<KT>::kPairs, kGroups = Cta<KT>::kGroups;
+    // row-pair tiles, element (mini m, row pair p, step i) at [tile_at<KT>(m, p, i)]
+    float4 X[kMinis * tile_m<KT>()];      // (delta r0, delta r1, delta*u r0, delta*u r1); later (ddelta r0, r1, du r0, r1)
+    float4 Y[kMinis * tile_m<KT>()];      // (dy r0, dy r1, D dy r0, D dy r1)
+    float4 Z[kMinis * tile_m<KT>()];      // (ln2 s' r0, ln2 s' r1, u s' r0, u s' r1) with s' = d softplus / d raw delta
     float2 Bd[kSub][kLn];                 // (B_n0, B_n0+1) per lane
     float2 Cd[kSub][kLn];
     float4 hs[kPairs][kSub / kMini - 1][kLn];   // state at the start of mini-chunks 0..2: (n0 r0, n0 r1, n0+1 r0, n0+1 r1)
     float st[kGroups * kStGroup];         // transposing tile of the row groups; reused for the dB/dC hand-over
 };
 
-template <typename T, bool kHasZ>
-__global__ void __launch_bounds__(kT, kMinCtas) scan_bwd_kernel(const ScanBwdArgs a) {
+template <typename T, bool kHasZ, int KT>
+__global__ void __launch_bounds__(KT, Cta<KT>::kMinCtas) scan_bwd_kernel(const ScanBwdArgs a) {
+    constexpr int kT = KT, kGroups = Cta<KT>::kGroups, kPairs = Cta<KT>::kPairs, kRowsB = Cta<KT>::kRowsB;
     constexpr int VEC = kMini;                           // global I/O in 4-element vectors (16 bytes fp32, 8 bytes bf16/fp16)
     constexpr int VPR = kSub / VEC;                      // vectors per row chunk: the 128 threads are 32 row pairs x 4 vectors
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    BwdSmem &s = *reinterpret_cast<BwdSmem *>(smem_raw);
+    BwdSmem<KT> &s = *reinterpret_cast<BwdSmem<KT> *>(smem_raw);
     const int tid = threadIdx.x;
     const int grp = tid >> 3, ln = tid & 7;
     const int n0 = 2 * ln;                               // first of this lane's two states
@@ -222,7 +233,7 @@ __global__ void __launch_bounds__(kT, kMinCtas) scan_bwd_kernel(const ScanBwdArg
             }
 #pragma unroll
             for (int i = 0; i < VEC; ++i) {
-                const int e = tile_at(col / kMini + i / kMini, rp, i % kMini);
+                const int e = tile_at<KT>(col / kMini + i / kMini, rp, i % kMini);
                 s.X[e] = make_float4(dv[0][i], dv[1][i], tu[0][i], tu[1][i]);
                 s.Y[e] = make_float4(gv[0][i], gv[1][i], dg[0][i], dg[1][i]);
                 s.Z[e] = make_float4(sk[0][i], sk[1][i], su[0][i], su[1][i]);
@@ -281,7 +292,7 @@ __global__ void __launch_bounds__(kT, kMinCtas) scan_bwd_kernel(const ScanBwdArg
                 for (int i = 0; i < kMini; ++i) {
                     const float2 Bv = s.Bd[m * kMini + i][ln];           // one load serves both row pairs
 #pragma unroll
-                    for (int q = 0; q < 2; ++q) fwd_step(s.X[tile_at(m, grp * 2 + q, i)], Bv, q, h[q], dtmp);
+                    for (int q = 0; q < 2; ++q) fwd_step(s.X[tile_at<KT>(m, grp * 2 + q, i)], Bv, q, h[q], dtmp);
                 }
             }
 #pragma unroll
@@ -301,7 +312,7 @@ __global__ void __launch_bounds__(kT, kMinCtas) scan_bwd_kernel(const ScanBwdArg
             }
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
-                const int e0 = tile_at(m, grp * 2 + q, 0);
+                const int e0 = tile_at<KT>(m, grp * 2 + q, 0);
                 float2 hist[kMini + 1][2], dec[kMini][2];
                 float4 xv[kMini];
                 if (m == kMinis - 1) {
@@ -366,16 +377,17 @@ __global__ void __launch_bounds__(kT, kMinCtas) scan_bwd_kernel(const ScanBwdArg
                 *reinterpret_cast<float4 *>(st_grp + (c * kLn + ln) * 4) = f;
             }
             __syncthreads();
-            {
+#pragma unroll
+            for (int t = tid; t < 128; t += kT) {                // 128 sums = (B|C, state, step)
                 float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
                 for (int gg = 0; gg < kGroups; gg += 4) {
-                    s0 += s.st[gg * kStGroup + tid];
-                    s1 += s.st[(gg + 1) * kStGroup + tid];
-                    s2 += s.st[(gg + 2) * kStGroup + tid];
-                    s3 += s.st[(gg + 3) * kStGroup + tid];
+                    s0 += s.st[gg * kStGroup + t];
+                    s1 += s.st[(gg + 1) * kStGroup + t];
+                    s2 += s.st[(gg + 2) * kStGroup + t];
+                    s3 += s.st[(gg + 3) * kStGroup + t];
                 }
-                const int c = tid >> 5, n = 2 * ((tid >> 2) & 7) + (c & 1), l = l0 + m * kMini + (tid & 3);
+                const int c = t >> 5, n = 2 * ((t >> 2) & 7) + (c & 1), l = l0 + m * kMini + (t & 3);
                 if (n < a.dstate && l < L) {
                     float *dst = c < 2 ? a.dB + b * a.dB_bs + g * a.dB_gs + n * a.dB_ns + l
                                        : a.dC + b * a.dC_bs + g * a.dC_gs + n * a.dC_ns + l;
@@ -391,7 +403,7 @@ __global__ void __launch_bounds__(kT, kMinCtas) scan_bwd_kernel(const ScanBwdArg
             float dd[2][VEC], du_[2][VEC];
 #pragma unroll
             for (int i = 0; i < VEC; ++i) {
-                const float4 o = s.X[tile_at(col / kMini + i / kMini, rp, i % kMini)];
+                const float4 o = s.X[tile_at<KT>(col / kMini + i / kMini, rp, i % kMini)];
                 dd[0][i] = o.x; dd[1][i] = o.y; du_[0][i] = o.z; du_[1][i] = o.w;
             }
 #pragma unroll
@@ -453,17 +465,28 @@ __global__ void __launch_bounds__(kT, kMinCtas) scan_bwd_kernel(const ScanBwdArg
     }
 }
 
-template <typename T>
-int run(const ScanBwdArgs &a, int batch, cudaStream_t stream) {
+template <typename T, int KT>
+int run_width(const ScanBwdArgs &a, int batch, cudaStream_t stream) {
     const int dpg = a.dim / a.n_groups;
-    dim3 grid(a.n_groups * ((dpg + kRowsB - 1) / kRowsB), batch);
-    const int smem = (int)sizeof(BwdSmem);
+    dim3 grid(a.n_groups * ((dpg + Cta<KT>::kRowsB - 1) / Cta<KT>::kRowsB), batch);
+    const int smem = (int)sizeof(BwdSmem<KT>);
     auto go = [&](auto kern) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        kern<<<grid, kT, smem, stream>>>(a);
+        kern<<<grid, KT, smem, stream>>>(a);
     };
-    if (a.z != nullptr) go(scan_bwd_kernel<T, true>); else go(scan_bwd_kernel<T, false>);
+    if (a.z != nullptr) go(scan_bwd_kernel<T, true, KT>); else go(scan_bwd_kernel<T, false, KT>);
     return check_launch("selective_scan_bwd");
+}
+
+template <typename T>
+int run(const ScanBwdArgs &a, int batch, cudaStream_t stream) {
+    // 64-thread CTAs (32 rows each, 7 per SM = 14 warps at 144 registers) beat the 128-thread CTAs of round 1 (3 per SM = 12
+    // warps at 168 registers) at every shape -- the kernel is latency-bound, two more resident warps and finer CTAs help:
+    // 3.23 -> 3.04 ms fp32 / 3.16 -> 2.92 ms bf16 at 256 x 2048 x 256, 0.34 -> 0.26 ms at the 32-latent training shape, whose
+    // grid also fits one wave now (1024 CTAs on 1036 slots instead of 512 on 444).  8 CTAs per SM at 128 registers (3.34 ms) and
+    // 32-thread CTAs (3.33 ms) were measured slower.  DIMSUM_SCAN_BWD_THREADS=128 runs the round-1 shape.
+    static const int forced = [] { const char *e = getenv("DIMSUM_SCAN_BWD_THREADS"); return e ? atoi(e) : 0; }();
+    return forced == 128 ? run_width<T, 128>(a, batch, stream) : run_width<T, 64>(a, batch, stream);
 }
 
 }  // namespace
