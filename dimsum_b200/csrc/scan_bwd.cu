@@ -28,7 +28,7 @@
 namespace dimsum {
 namespace {
 
-// threads per CTA: 64 (32 rows; 7 CTAs = 14 warps per SM at 144 registers; the default) or 128 (64 rows; 3 CTAs = 12 warps per
+// threads per CTA: 64 (32 rows; 128 registers, 8 CTAs = 16 warps per SM; the default) or 128 (64 rows; 3 CTAs = 12 warps per
 // SM at 168 registers, round 1)
 constexpr int kLn = 8;                     // lanes per row group (2 states each)
 template <int KT> struct Cta {
@@ -480,11 +480,12 @@ int run_width(const ScanBwdArgs &a, int batch, cudaStream_t stream) {
 
 template <typename T>
 int run(const ScanBwdArgs &a, int batch, cudaStream_t stream) {
-    // 64-thread CTAs (32 rows each, 7 per SM = 14 warps at 144 registers) beat the 128-thread CTAs of round 1 (3 per SM = 12
-    // warps at 168 registers) at every shape -- the kernel is latency-bound, two more resident warps and finer CTAs help:
+    // 64-thread CTAs (32 rows each; under __launch_bounds__(64, 7) ptxas settles on 128 registers, so 8 CTAs = 16 warps are
+    // resident per SM) beat the 128-thread CTAs of round 1 (3 per SM = 12 warps at 168 registers) at every shape -- the kernel
+    // is latency-bound, more resident warps and finer CTAs help:
     // 3.23 -> 3.04 ms fp32 / 3.16 -> 2.92 ms bf16 at 256 x 2048 x 256, 0.34 -> 0.26 ms at the 32-latent training shape, whose
-    // grid also fits one wave now (1024 CTAs on 1036 slots instead of 512 on 444).  8 CTAs per SM at 128 registers (3.34 ms) and
-    // 32-thread CTAs (3.33 ms) were measured slower.  DIMSUM_SCAN_BWD_THREADS=128 runs the round-1 shape.
+    // grid also fits one wave now (1024 CTAs instead of 512 on 444 slots).  Asking for 8 CTAs per SM in the launch bound gave a
+    // slower schedule (3.34 ms) and so did 32-thread CTAs (3.33 ms).  DIMSUM_SCAN_BWD_THREADS=128 runs the round-1 shape.
     static const int forced = [] { const char *e = getenv("DIMSUM_SCAN_BWD_THREADS"); return e ? atoi(e) : 0; }();
     return forced == 128 ? run_width<T, 128>(a, batch, stream) : run_width<T, 64>(a, batch, stream);
 }
