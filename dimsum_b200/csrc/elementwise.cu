@@ -252,6 +252,14 @@ __global__ void __launch_bounds__(256) cfg_euler_kernel(const dimsum_cfg_euler_p
     float *d0 = reinterpret_cast<float *>(p.x_new) + r * per_row + e;
     *reinterpret_cast<float4 *>(d0) = *reinterpret_cast<const float4 *>(o);
     *reinterpret_cast<float4 *>(d0 + p.half_batch * per_row) = *reinterpret_cast<const float4 *>(o);
+    if (p.v_out != nullptr) {                                   // the guided drift itself, for callers that integrate differently
+        float vv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) vv[i] = __fadd_rn(u[i], __fmul_rn(s, __fsub_rn(c[i], u[i])));
+        float *v0 = reinterpret_cast<float *>(p.v_out) + r * per_row + e;
+        *reinterpret_cast<float4 *>(v0) = *reinterpret_cast<const float4 *>(vv);
+        *reinterpret_cast<float4 *>(v0 + p.half_batch * per_row) = *reinterpret_cast<const float4 *>(vv);
+    }
 }
 
 // column sums over the tokens of a batch row: CTA = (128 channels, batch row); 8 warps stride over the tokens, a lane

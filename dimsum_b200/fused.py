@@ -149,7 +149,7 @@ def gelu_mul(x12):
     return y.view(shape[:-1] + (H,))
 
 
-def cfg_euler_step(x, model_out, cfg_scale, dt, out=None):
+def cfg_euler_step(x, model_out, cfg_scale, dt, out=None, v_out=None):
     """x_new = x + dt * (uncond + s * (cond - uncond)) on both halves of a CFG batch, one pass (models_dim.py:1886-1902 +
     integrators.py:98-111).  x (2n, C, H, W) fp32; model_out (2n, >= C, H, W), cond rows first; dt: fp32 CUDA scalar tensor."""
     n2, C, H, W = x.shape
@@ -164,6 +164,10 @@ def cfg_euler_step(x, model_out, cfg_scale, dt, out=None):
         p.half_batch, p.channels, p.hw, p.out_dtype, p.out_row_stride = n2 // 2, C, H * W, _DT[model_out.dtype], model_out.stride(0)
         p.cfg_scale = float(cfg_scale)
         p.model_out, p.x, p.dt, p.x_new = model_out.data_ptr(), x.data_ptr(), dt.data_ptr(), out.data_ptr()
+        if v_out is not None:
+            if v_out.shape != x.shape or v_out.dtype != torch.float32 or not v_out.is_contiguous():
+                raise RuntimeError("cfg_euler_step: v_out must be contiguous fp32 with the shape of x")
+            p.v_out = v_out.data_ptr()
         _lib.call("dimsum_cfg_euler_step", p, torch.cuda.current_stream(x.device).cuda_stream)
     return out
 

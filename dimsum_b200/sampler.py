@@ -77,8 +77,8 @@ class GraphedCfgStep:
                 from . import fused
                 half = self.x[: len(self.x) // 2]
                 out = model.forward(torch.cat([half, half], dim=0), self.t, self.y)
-                fused.cfg_euler_step(self.x, out, cfg_scale, self.dt, out=self.x_new)
-                self.v = None
+                self.v = torch.empty_like(self.x)
+                fused.cfg_euler_step(self.x, out, cfg_scale, self.dt, out=self.x_new, v_out=self.v)
             else:
                 self.v = model.forward_with_cfg(self.x, self.t, self.y, cfg_scale=cfg_scale)
         self.fused = fused_ok
@@ -87,10 +87,7 @@ class GraphedCfgStep:
         self.launches_per_replay = _lib.launch_count() - before
 
     def __call__(self, x, t):
-        """-> v = forward_with_cfg(x, t, y) (the drift).  With the fused graph the drift is recovered from the Euler update."""
-        if self.fused:
-            one = torch.ones((), device=self.x.device)
-            return self.euler(x, t, one) - x
+        """-> v = forward_with_cfg(x, t, y) (the drift)."""
         self.x.copy_(x, non_blocking=True)
         self.t.copy_(t, non_blocking=True)
         self.graph.replay()

@@ -320,13 +320,14 @@ int dimsum_gelu_mul(const dimsum_gelu_mul_params *p, void *stream);
  *   model_out : (2 * half_batch, >= channels, H, W) in out_dtype, row (sample) stride out_row_stride; cond rows first
  *   x, x_new  : (2 * half_batch, channels, H, W) fp32 contiguous (x_new may alias x); dt: fp32 scalar in DEVICE memory (so the
  *               step can sit inside a CUDA graph whose grid position changes between replays)
+ *   v_out     : NULL, or (2 * half_batch, channels, H, W) fp32: also store the guided drift v (both halves)
  */
 typedef struct {
     int64_t half_batch, channels, hw, out_dtype, out_row_stride;
     float cfg_scale;
     const void *model_out, *x;
     const float *dt;
-    void *x_new;
+    void *x_new, *v_out;
 } dimsum_cfg_euler_params;
 
 int dimsum_cfg_euler_step(const dimsum_cfg_euler_params *p, void *stream);

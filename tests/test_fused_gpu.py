@@ -226,12 +226,14 @@ def test_cfg_euler_step_matches_forward_with_cfg_plus_euler(out_dtype):
     x = torch.cat([half, half])
     out = torch.randn(2 * n, C, H, H, generator=g, device="cuda").to(out_dtype)
     dt = torch.tensor(1.0 / 249, device="cuda")
-    got = fused.cfg_euler_step(x, out, 4.0, dt)
+    v_buf = torch.empty_like(x)
+    got = fused.cfg_euler_step(x, out, 4.0, dt, v_out=v_buf)
     o = out.float()
     cond, uncond = o[:n], o[n:]
     v = uncond + 4.0 * (cond - uncond)
     want = x + dt * torch.cat([v, v])
     assert torch.equal(got, want)
     assert torch.equal(got[:n], got[n:])
+    assert torch.equal(v_buf, torch.cat([v, v]))
     with pytest.raises(RuntimeError):
         fused.cfg_euler_step(x.half(), out, 4.0, dt)
