@@ -49,6 +49,9 @@ template <int KT> __device__ __host__ constexpr int tile_m() { return Cta<KT>::k
 // element (mini m, row pair p, step i) of a row-pair tile
 template <int KT>
 __device__ __forceinline__ constexpr int tile_at(int m, int p, int i) { return m * tile_m<KT>() + (p >> 1) * kTileG + (p & 1) * kMini + i; }
+constexpr bool kShflReduce = false;        // true: per-step 16-state dot products by recursive-halving warp shuffles instead of the shared
+                                           // transposing tile.  Measured: 3.04 -> 2.99 ms fp32, 2.92 -> 2.86 ms bf16 at 256 x
+                                           // 2048 x 256, 0.242 -> 0.264 ms bf16 at the training shape: shuffles ride the same LSU pipe; not enabled
 constexpr int kStLane = 20;                // words per lane record of the transposing tile (8 packed values + pad)
 constexpr int kStGroup = kLn * kStLane + 16;   // words per group: odd multiple of 16 -> the two groups of a half warp use disjoint banks
 
@@ -330,6 +333,7 @@ __global__ void __launch_bounds__(KT, Cta<KT>::kMinCtas) scan_bwd_kernel(const S
                     xv[i] = s.X[e0 + i];
                     fwd_step(xv[i], Bm[i], q, hist[i + 1], dec[i]);
                 }
+                float4 pq_prev = make_float4(0.f, 0.f, 0.f, 0.f), pq_a = pq_prev, pq_b = pq_prev;
 #pragma unroll
                 for (int i = kMini - 1; i >= 0; --i) {
                     const float2 dyv = *reinterpret_cast<const float2 *>(&s.Y[e0 + i]);
@@ -348,24 +352,53 @@ __global__ void __launch_bounds__(KT, Cta<KT>::kMinCtas) scan_bwd_kernel(const S
                         accB[i][si] = fmaf(gl.y, dtu.y, fmaf(gl.x, dtu.x, accB[i][si]));
                         accC[i][si] = fmaf(hist[i + 1][si].y, dyv.y, fmaf(hist[i + 1][si].x, dyv.x, accC[i][si]));
                     }
-                    *reinterpret_cast<float4 *>(st_grp + ln * kStLane + 4 * i) = make_float4(P.x, P.y, Q.x, Q.y);
+                    if (!kShflReduce) {
+                        *reinterpret_cast<float4 *>(st_grp + ln * kStLane + 4 * i) = make_float4(P.x, P.y, Q.x, Q.y);
+                    } else {
+                        // recursive halving over the 8 lanes of the group, folded into the step loop so that at most two
+                        // (P, Q) sets are alive: steps 3|2 and 1|0 are split over lane bit 2 as soon as both exist
+                        const float4 cur = make_float4(P.x, P.y, Q.x, Q.y);
+                        if (i & 1) {
+                            pq_prev = cur;
+                        } else {
+                            const bool hi = (ln & 4) != 0;                    // hi lanes keep step i, low lanes step i + 1
+                            const float4 send = hi ? pq_prev : cur, keep = hi ? cur : pq_prev;
+                            const float4 got = make_float4(__shfl_xor_sync(0xffffffffu, send.x, 4), __shfl_xor_sync(0xffffffffu, send.y, 4),
+                                                           __shfl_xor_sync(0xffffffffu, send.z, 4), __shfl_xor_sync(0xffffffffu, send.w, 4));
+                            const float4 sum = make_float4(keep.x + got.x, keep.y + got.y, keep.z + got.z, keep.w + got.w);
+                            if (i == 2) pq_a = sum; else pq_b = sum;
+                        }
+                    }
                 }
-                __syncwarp();
-                // transpose: lane j = 2 i + w collects sum_n of value w (0: e A, 1: g B) of step i, both rows
-                float2 tot = *reinterpret_cast<const float2 *>(st_grp + 2 * ln);
+                float2 tot;
+                if (!kShflReduce) {
+                    __syncwarp();
+                    // transpose: lane j = 2 i + w collects sum_n of value w (0: e A, 1: g B) of step i, both rows
+                    tot = *reinterpret_cast<const float2 *>(st_grp + 2 * ln);
 #pragma unroll
-                for (int o = 1; o < kLn; ++o) tot = add2(tot, *reinterpret_cast<const float2 *>(st_grp + o * kStLane + 2 * ln));
+                    for (int o = 1; o < kLn; ++o) tot = add2(tot, *reinterpret_cast<const float2 *>(st_grp + o * kStLane + 2 * ln));
+                } else {
+                    const bool hi1 = (ln & 2) != 0;                           // lane bit 1: steps 1|0 (set b) vs 3|2 (set a)
+                    const float4 send = hi1 ? pq_a : pq_b, keep = hi1 ? pq_b : pq_a;
+                    const float4 k2 = make_float4(keep.x + __shfl_xor_sync(0xffffffffu, send.x, 2), keep.y + __shfl_xor_sync(0xffffffffu, send.y, 2),
+                                                  keep.z + __shfl_xor_sync(0xffffffffu, send.z, 2), keep.w + __shfl_xor_sync(0xffffffffu, send.w, 2));
+                    const bool odd = (ln & 1) != 0;                           // lane bit 0: Q (odd) vs P (even)
+                    const float sx = odd ? k2.x : k2.z, sy = odd ? k2.y : k2.w;
+                    tot = make_float2((odd ? k2.z : k2.x) + __shfl_xor_sync(0xffffffffu, sx, 1),
+                                      (odd ? k2.w : k2.y) + __shfl_xor_sync(0xffffffffu, sy, 1));
+                }
                 const float qx = __shfl_down_sync(0xffffffffu, tot.x, 1), qy = __shfl_down_sync(0xffffffffu, tot.y, 1);
                 if ((ln & 1) == 0) {
                     // ddelta = (ln2 sum_n e A2 + u sum_n g B) s' ; du = delta sum_n g B + D dy
-                    const int e = e0 + (ln >> 1);
+                    // (shuffle reduction: lane bits 1, 2 select step 3 - (2 bit1 + bit2); tile reduction: step = lane / 2)
+                    const int e = e0 + (kShflReduce ? 3 - (2 * ((ln >> 1) & 1) + ((ln >> 2) & 1)) : (ln >> 1));
                     const float4 xr = s.X[e], yr = s.Y[e], zr = s.Z[e];
                     const float dd0 = fmaf(zr.z, qx, tot.x * zr.x), dd1 = fmaf(zr.w, qy, tot.y * zr.y);
                     s.X[e] = make_float4(dd0, dd1, fmaf(xr.x, qx, yr.z), fmaf(xr.y, qy, yr.w));
                     dbias_acc[q].x += dd0;
                     dbias_acc[q].y += dd1;
                 }
-                __syncwarp();
+                if (!kShflReduce) __syncwarp();
             }
             // dB / dC of the 4 steps: each group leaves its 64 sums in its own tile, 128 threads add the 16 groups
             // (thread = (B|C, state, step), steps fastest so that 4 lanes hit 16 contiguous bytes), one atomic each
