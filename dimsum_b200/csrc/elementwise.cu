@@ -275,7 +275,10 @@ __global__ void __launch_bounds__(256) colsum_kernel(const dimsum_colsum_params 
         for (int l = warp; l < p.seqlen; l += 8) {
             float g[4], x[4];
             ld_rt<4>(p.g, (int)p.g_dtype, b * p.g_batch_stride + (int64_t)l * p.g_token_stride + c0, g);
-            if (want_x) ld_rt<4>(p.x, (int)p.x_dtype, b * p.x_batch_stride + (int64_t)l * p.x_token_stride + c0, x);
+            if (want_x) {
+                const int64_t lx = p.x_idx != nullptr ? (int64_t)__ldg(p.x_idx + l) : (int64_t)l;
+                ld_rt<4>(p.x, (int)p.x_dtype, b * p.x_batch_stride + lx * p.x_token_stride + c0, x);
+            }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 sg[i] += g[i];

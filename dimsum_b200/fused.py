@@ -69,8 +69,8 @@ def gate_residual(x, gate, m, idx=None, out_dtype=None):
     return out
 
 
-def add_rmsnorm(x, residual, weight, eps, want_residual=True):
-    """-> (y, res_out): res_out = x + residual in fp32, y = rmsnorm(res_out) * weight in x.dtype."""
+def add_rmsnorm(x, residual, weight, eps, want_residual=True, out_dtype=None):
+    """-> (y, res_out): res_out = x + residual in fp32, y = rmsnorm(res_out) * weight in `out_dtype` (default x.dtype)."""
     shape = x.shape
     x2 = x.reshape(-1, shape[-1])
     if x2.stride(1) != 1:
@@ -81,17 +81,26 @@ def add_rmsnorm(x, residual, weight, eps, want_residual=True):
             raise RuntimeError("add_rmsnorm: residual must be fp32 with the shape of x")
         residual = residual.contiguous()
     w = weight.float().contiguous()
-    y = torch.empty((rows, C), device=x.device, dtype=x.dtype)
+    out_dtype = out_dtype or x.dtype
+    y = torch.empty((rows, C), device=x.device, dtype=out_dtype)
     res_out = torch.empty((rows, C), device=x.device, dtype=torch.float32) if want_residual else None
     with torch.cuda.device(x.device):
-        p = _lib.RmsnormParams()
-        p.rows, p.channels, p.dtype = rows, C, _DT[x.dtype]
+        if out_dtype == x.dtype:
+            p = _lib.RmsnormParams()
+            p.rows, p.channels, p.dtype = rows, C, _DT[x.dtype]
+            entry = "dimsum_add_rmsnorm"
+        else:                       # same kernel through the entry point that takes the two dtypes separately (no modulate)
+            p = _lib.NormModulateParams()
+            p.rows, p.channels, p.rows_per_batch = rows, C, 1
+            p.x_dtype, p.aux_dtype, p.y_dtype, p.norm_kind = _DT[x.dtype], _DT[torch.float32], _DT[out_dtype], 0
+            p.shift = p.scale = None
+            entry = "dimsum_norm_modulate"
         p.x_row_stride, p.y_row_stride = x2.stride(0), y.stride(0)
         p.x, p.weight, p.y = x2.data_ptr(), w.data_ptr(), y.data_ptr()
         p.residual = residual.data_ptr() if residual is not None else None
         p.res_out = res_out.data_ptr() if res_out is not None else None
         p.eps = eps
-        _lib.call("dimsum_add_rmsnorm", p, torch.cuda.current_stream(x.device).cuda_stream)
+        _lib.call(entry, p, torch.cuda.current_stream(x.device).cuda_stream)
     return y.view(shape), (res_out.view(shape) if res_out is not None else None)
 
 
@@ -175,8 +184,9 @@ def cfg_euler_step(x, model_out, cfg_scale, dt, out=None, v_out=None):
 # ---------------------------------------------------------------------------------------------------
 # training: the same kernels under autograd
 # ---------------------------------------------------------------------------------------------------
-def token_colsum(g, x=None, want_sum_g=True, out_dtype=None):
-    """-> (sum_l g[b, l, :], sum_l g[b, l, :] * x[b, l, :]) as (batch, channels) tensors (None where not requested)."""
+def token_colsum(g, x=None, want_sum_g=True, out_dtype=None, x_idx=None):
+    """-> (sum_l g[b, l, :], sum_l g[b, l, :] * x[b, x_idx[l], :]) as (batch, channels) tensors (None where not requested);
+    `x_idx` (int32 token table, default identity) pairs g's row l with x's row x_idx[l]."""
     _rows(g, "g")
     if x is not None:
         _rows(x, "x")
@@ -197,6 +207,7 @@ def token_colsum(g, x=None, want_sum_g=True, out_dtype=None):
         p.g, p.x = g.data_ptr(), x.data_ptr() if x is not None else None
         p.sum_g = sum_g.data_ptr() if sum_g is not None else None
         p.sum_gx = sum_gx.data_ptr() if sum_gx is not None else None
+        p.x_idx = _idx(x_idx, L) if x is not None else None
         _lib.call("dimsum_token_colsum", p, torch.cuda.current_stream(g.device).cuda_stream)
     return sum_g, sum_gx
 
@@ -206,36 +217,40 @@ def _rows_ok(t):
 
 
 class _ModulateFn(torch.autograd.Function):
-    """y = x * (1 + scale[:, None]) + shift[:, None] (models_dim.py:34-35) in the promoted dtype of x and scale."""
+    """y[l] = x[idx[l]] * (1 + scale[:, None]) + shift[:, None] (models_dim.py:34-35, with the scan order of
+    models_dim.py:1498-1524 folded into the row index) in `out_dtype` (default: the promoted dtype of x and scale).
+    `inv` is the inverse table of `idx`; both None = natural order."""
 
     @staticmethod
-    def forward(ctx, x, shift, scale):
+    def forward(ctx, x, shift, scale, idx, inv, out_dtype):
         x = _rows_ok(x)
         ctx.save_for_backward(x, scale)
-        ctx.shift_dtype = shift.dtype
-        return modulate(x, shift, scale, out_dtype=torch.promote_types(x.dtype, scale.dtype))
+        ctx.shift_dtype, ctx.idx, ctx.inv = shift.dtype, idx, inv
+        return modulate(x, shift, scale, idx, out_dtype=out_dtype or torch.promote_types(x.dtype, scale.dtype))
 
     @staticmethod
     def backward(ctx, gy):
         x, scale = ctx.saved_tensors
         gy = _rows_ok(gy)
-        zero = torch.zeros(scale.shape, device=scale.device, dtype=scale.dtype)
-        if zero.stride(0) != scale.stride(0):
-            scale = scale.contiguous()
-        gx = modulate(gy, zero, scale, out_dtype=x.dtype) if ctx.needs_input_grad[0] else None
-        gshift, gscale = token_colsum(gy, x, want_sum_g=True, out_dtype=ctx.shift_dtype)
-        return gx, gshift, gscale
+        gx = None
+        if ctx.needs_input_grad[0]:             # gx[j] = gy[inv[j]] * (1 + scale): the same kernel through the inverse table
+            zero = torch.zeros(scale.shape, device=scale.device, dtype=scale.dtype)
+            sc = scale if zero.stride(0) == scale.stride(0) else scale.contiguous()
+            gx = modulate(gy, zero, sc, ctx.inv, out_dtype=x.dtype)
+        gshift, gscale = token_colsum(gy, x, want_sum_g=True, out_dtype=ctx.shift_dtype, x_idx=ctx.idx)
+        return gx, gshift, gscale, None, None, None
 
 
 class _GateResidualFn(torch.autograd.Function):
-    """out = x + gate[:, None] * m (models_dim.py:1510-1512) in the promoted dtype of x and gate."""
+    """out[l] = x[l] + gate[:, None] * m[idx[l]] (models_dim.py:1510-1512; `idx` undoes the scan order, `inv` is its inverse)
+    in `out_dtype` (default: the promoted dtype of x and gate)."""
 
     @staticmethod
-    def forward(ctx, x, gate, m):
+    def forward(ctx, x, gate, m, idx, inv, out_dtype):
         x, m = _rows_ok(x), _rows_ok(m)
         ctx.save_for_backward(gate, m)
-        ctx.x_dtype = x.dtype
-        return gate_residual(x, gate, m, out_dtype=torch.promote_types(x.dtype, gate.dtype))
+        ctx.x_dtype, ctx.idx, ctx.inv = x.dtype, idx, inv
+        return gate_residual(x, gate, m, idx, out_dtype=out_dtype or torch.promote_types(x.dtype, gate.dtype))
 
     @staticmethod
     def backward(ctx, gy):
@@ -244,13 +259,13 @@ class _GateResidualFn(torch.autograd.Function):
         gx = gy if gy.dtype == ctx.x_dtype else gy.to(ctx.x_dtype)
         gm = None
         if ctx.needs_input_grad[2]:
-            # gy * gate = gy * (1 + (gate - 1)) + 0.  `gate - 1` is formed in fp32: rounded to bf16 it would quantise the
-            # effective gate to multiples of 2^-8 (a gate of 1e-3 would become 0); the kernel takes the aux dtype
-            # independently of gy's
+            # gm[k] = gate * gy[inv[k]] = gy * (1 + (gate - 1)) + 0.  `gate - 1` is formed in fp32: rounded to bf16 it would
+            # quantise the effective gate to multiples of 2^-8 (a gate of 1e-3 would become 0); the kernel takes the aux
+            # dtype independently of gy's
             gm1 = (gate.float() - 1).contiguous()
-            gm = modulate(gy, torch.zeros_like(gm1), gm1, out_dtype=m.dtype)
-        _, ggate = token_colsum(gy, m, want_sum_g=False, out_dtype=gate.dtype)
-        return gx, ggate, gm
+            gm = modulate(gy, torch.zeros_like(gm1), gm1, ctx.inv, out_dtype=m.dtype)
+        _, ggate = token_colsum(gy, m, want_sum_g=False, out_dtype=gate.dtype, x_idx=ctx.idx)
+        return gx, ggate, gm, None, None, None
 
 
 class _GeluMulFn(torch.autograd.Function):
@@ -286,8 +301,8 @@ class _AddRmsNormFn(torch.autograd.Function):
     """(y, h) = (rmsnorm(x + residual) * weight, x + residual in fp32); backward by `dimsum_add_rmsnorm_bwd`."""
 
     @staticmethod
-    def forward(ctx, x, residual, weight, eps):
-        y, h = add_rmsnorm(x, residual, weight, eps, want_residual=True)
+    def forward(ctx, x, residual, weight, eps, out_dtype=None):
+        y, h = add_rmsnorm(x, residual, weight, eps, want_residual=True, out_dtype=out_dtype)
         ctx.save_for_backward(h, weight)
         ctx.eps, ctx.x_dtype, ctx.has_res = eps, x.dtype, residual is not None
         return y, h
@@ -321,20 +336,26 @@ class _AddRmsNormFn(torch.autograd.Function):
             p.dres_out = dres.data_ptr() if dres is not None else None
             p.eps = ctx.eps
             _lib.call("dimsum_add_rmsnorm_bwd", p, torch.cuda.current_stream(h.device).cuda_stream)
-        return dx.view(shape), (dres.view(shape) if dres is not None else None), part.sum(0).to(weight.dtype), None
+        return dx.view(shape), (dres.view(shape) if dres is not None else None), part.sum(0).to(weight.dtype), None, None
 
 
-def add_rmsnorm_fn(x, residual, weight, eps):
-    """-> (y, h) with autograd: y = rmsnorm(x + residual) * weight in x.dtype, h = x + residual in fp32."""
-    return _AddRmsNormFn.apply(x, residual, weight, eps)
+def add_rmsnorm_fn(x, residual, weight, eps, out_dtype=None):
+    """-> (y, h) with autograd: y = rmsnorm(x + residual) * weight in `out_dtype` (default x.dtype), h = x + residual in fp32."""
+    return _AddRmsNormFn.apply(x, residual, weight, eps, out_dtype)
 
 
-def modulate_fn(x, shift, scale):
-    return _ModulateFn.apply(x, shift, scale)
+def modulate_fn(x, shift, scale, idx=None, inv=None, out_dtype=None):
+    """Differentiable `modulate`; with a token table `idx` (and its inverse `inv`) the output row l is computed from row idx[l]."""
+    if (idx is None) != (inv is None):
+        raise RuntimeError("modulate_fn: idx and inv come together")
+    return _ModulateFn.apply(x, shift, scale, idx, inv, out_dtype)
 
 
-def gate_residual_fn(x, gate, m):
-    return _GateResidualFn.apply(x, gate, m if m.dtype == gate.dtype else m.to(gate.dtype))
+def gate_residual_fn(x, gate, m, idx=None, inv=None, out_dtype=None):
+    """Differentiable `gate_residual`; with a token table `idx` (and its inverse `inv`) row l adds gate * m[idx[l]]."""
+    if (idx is None) != (inv is None):
+        raise RuntimeError("gate_residual_fn: idx and inv come together")
+    return _GateResidualFn.apply(x, gate, m if m.dtype == gate.dtype else m.to(gate.dtype), idx, inv, out_dtype)
 
 
 def gelu_mul_fn(x12):

@@ -20,7 +20,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import causal_conv1d_cuda, selective_scan_cuda
+from . import amp, causal_conv1d_cuda, selective_scan_cuda
 from .selective_scan_interface import _rows_times_wt, mamba_inner_fn
 
 
@@ -155,7 +155,8 @@ class Mamba(nn.Module):
     def _mix(self, hidden_states, order):
         batch, seqlen, _ = hidden_states.shape
         # in_proj with the transpose folded in: (2*d_inner, B*L) viewed as (B, 2*d_inner, L), L contiguous
-        xz = (self.in_proj.weight @ hidden_states.reshape(batch * seqlen, -1).t()).view(-1, batch, seqlen).transpose(0, 1)
+        xz = amp.weight_times_rows_t(self.in_proj.weight, hidden_states.reshape(batch * seqlen, -1))
+        xz = xz.view(-1, batch, seqlen).transpose(0, 1)
         if self.in_proj.bias is not None:
             xz = xz + self.in_proj.bias.to(xz.dtype).view(1, -1, 1)
         A = -torch.exp(self.A_log.float())

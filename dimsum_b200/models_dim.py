@@ -24,7 +24,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import fused
+from . import amp, fused
 from . import scanning_orders as so
 from .attention import attention, attention_supported
 from .mamba_simple import CondMamba
@@ -50,14 +50,19 @@ def _train_fused_ok(x, *others):
             and all(t.dtype in _GLUE_DTYPES for t in (x,) + others))
 
 
-def _mod(x, shift, scale, idx=None):
+def _amp_dtype():
+    """Under autocast the consumer of a glue kernel's output is a low-precision GEMM: emit its input dtype directly instead
+    of an fp32 tensor that autocast would re-read and cast (same single rounding, one pass less forward and backward)."""
+    return torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else None
+
+
+def _mod(x, shift, scale, idx=None, inv=None):
+    """modulate(x[idx], shift, scale); every caller feeds the result to a GEMM.  `inv` is the inverse table of `idx`."""
     if _fused_ok(x):
-        # under autocast the consumer is a low-precision GEMM: emit its input dtype directly (no separate cast pass)
-        out_dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else None
-        return fused.modulate(x, shift, scale, idx, out_dtype=out_dtype)
-    assert idx is None
+        return fused.modulate(x, shift, scale, idx, out_dtype=_amp_dtype())
     if _train_fused_ok(x, shift, scale):
-        return fused.modulate_fn(x, shift, scale)
+        return fused.modulate_fn(x, shift, scale, idx, inv, out_dtype=_amp_dtype())
+    assert idx is None
     return modulate(x, shift, scale)
 
 
@@ -67,25 +72,36 @@ def _norm_mod(norm, x, shift, scale, residual=None):
     if (_fused_ok(x) and x.dim() == 3 and x.dtype in (torch.float32, torch.bfloat16, torch.float16)
             and (residual is None or residual.dtype == torch.float32)
             and (is_rms or (isinstance(norm, nn.LayerNorm) and norm.weight is None and norm.bias is None))):
-        out_dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else None
         y, h = fused.norm_modulate(x, residual, norm.weight if is_rms else None, norm.eps, shift, scale,
-                                   layer_norm=not is_rms, out_dtype=out_dtype, want_residual=residual is not None)
+                                   layer_norm=not is_rms, out_dtype=_amp_dtype(), want_residual=residual is not None)
         return y, (h if residual is not None else x)
+    if (is_rms and residual is not None and residual.dtype == torch.float32 and _train_fused_ok(x, shift, scale)
+            and x.shape[-1] <= 1024 and norm.weight.dtype == torch.float32 and torch.is_grad_enabled()):
+        # recorded pass: the residual add rides on the norm kernel (fp32 sum out, fp32 normalised rows), then modulate
+        n, h = fused.add_rmsnorm_fn(x, residual, norm.weight, norm.eps, out_dtype=torch.float32)
+        return _mod(n, shift, scale), h
     h = x if residual is None else x + residual
     return _mod(norm(h), shift, scale), h
 
 
-def _gated(x, gate, m, idx=None, feeds_gemm=False):
+def _gated(x, gate, m, idx=None, inv=None, feeds_gemm=False):
+    """x + gate * m[idx]; `inv` is the inverse table of `idx`.  A result that only feeds low-precision GEMMs under autocast is
+    emitted in their dtype (no cast pass)."""
     if _fused_ok(x):
         if m.dtype != gate.dtype:
             m = m.to(gate.dtype)
-        # a result that only feeds low-precision GEMMs under autocast is emitted in their dtype (no cast pass)
-        out_dtype = torch.get_autocast_dtype("cuda") if feeds_gemm and torch.is_autocast_enabled() else None
-        return fused.gate_residual(x, gate, m, idx, out_dtype=out_dtype)
-    assert idx is None
+        return fused.gate_residual(x, gate, m, idx, out_dtype=_amp_dtype() if feeds_gemm else None)
     if _train_fused_ok(x, gate, m) and m.shape == x.shape:
-        return fused.gate_residual_fn(x, gate, m)
+        return fused.gate_residual_fn(x, gate, m, idx, inv, out_dtype=_amp_dtype() if feeds_gemm else None)
+    assert idx is None
     return x + gate.unsqueeze(1) * m
+
+
+class Linear(nn.Linear):
+    """nn.Linear whose GEMMs run on the bf16 shadow of the weight when one is attached (`amp.Bf16Shadows`, training)."""
+
+    def forward(self, x):
+        return amp.linear(x, self.weight, self.bias)
 
 
 class RMSNorm(nn.Module):
@@ -119,7 +135,7 @@ class RMSNorm(nn.Module):
 class TimestepEmbedder(nn.Module):
     def __init__(self, hidden_size, frequency_embedding_size=256):
         super().__init__()
-        self.mlp = nn.Sequential(nn.Linear(frequency_embedding_size, hidden_size), nn.SiLU(), nn.Linear(hidden_size, hidden_size))
+        self.mlp = nn.Sequential(Linear(frequency_embedding_size, hidden_size), nn.SiLU(), Linear(hidden_size, hidden_size))
         self.frequency_embedding_size = frequency_embedding_size
 
     @staticmethod
@@ -165,16 +181,48 @@ class PatchEmbed(nn.Module):
         return self.proj(x).flatten(2).transpose(1, 2)
 
 
+class _QkvSplitFn(torch.autograd.Function):
+    """(B, N, 3*H*D) -> q, k, v as (B, H, N, D) views, like `.view(B, N, 3, H, D).permute(2, 0, 3, 1, 4).unbind(0)`
+    (attention_fusion.py:63-70).  Autograd's own backward of that chain stacks the three gradients into a (3, B, H, N, D)
+    tensor and then permutes it into a second copy -- two slow strided passes per attention; here each gradient is written
+    once, straight into its slot of the (B, N, 3, H, D) gradient of the projection."""
+
+    @staticmethod
+    def forward(ctx, qkv, num_heads):
+        B, N, C3 = qkv.shape
+        ctx.shape = (B, N, num_heads, C3 // 3 // num_heads)
+        return qkv.view(B, N, 3, num_heads, -1).permute(2, 0, 3, 1, 4).unbind(0)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        B, N, H, D = ctx.shape
+        ref = next(g for g in grads if g is not None)
+        out = torch.empty((B, N, 3, H, D), device=ref.device, dtype=ref.dtype)
+        for i, g in enumerate(grads):
+            if g is None:
+                out[:, :, i].zero_()
+            else:
+                out[:, :, i].copy_(g.transpose(1, 2))
+        return out.view(B, N, 3 * H * D), None
+
+
+def _split_qkv(qkv, num_heads):
+    if qkv.requires_grad and torch.is_grad_enabled():
+        return _QkvSplitFn.apply(qkv, num_heads)
+    B, N, C3 = qkv.shape
+    return qkv.view(B, N, 3, num_heads, C3 // 3 // num_heads).permute(2, 0, 3, 1, 4).unbind(0)
+
+
 class Attention(nn.Module):
     def __init__(self, dim, num_heads=8, qkv_bias=False):
         super().__init__()
         self.num_heads, self.head_dim = num_heads, dim // num_heads
-        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
-        self.proj = nn.Linear(dim, dim)
+        self.qkv = Linear(dim, dim * 3, bias=qkv_bias)
+        self.proj = Linear(dim, dim)
 
     def forward(self, x):
         B, N, C = x.shape
-        q, k, v = self.qkv(x).view(B, N, 3, self.num_heads, self.head_dim).permute(2, 0, 3, 1, 4).unbind(0)
+        q, k, v = _split_qkv(self.qkv(x), self.num_heads)
         if attention_supported(q, k, v):          # fp32 sampling with TF32 allowed: the TMA + tcgen05 kernel of this repo
             return self.proj(attention(q, k, v))  # already (B, N, C): no transpose copy
         return self.proj(F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, N, C))
@@ -183,8 +231,8 @@ class Attention(nn.Module):
 class GatedMLP(nn.Module):
     def __init__(self, in_features, hidden_features, act_layer, bias=True):
         super().__init__()
-        self.w12 = nn.Linear(in_features, 2 * hidden_features, bias=bias)
-        self.w3 = nn.Linear(hidden_features, in_features, bias=bias)
+        self.w12 = Linear(in_features, 2 * hidden_features, bias=bias)
+        self.w3 = Linear(hidden_features, in_features, bias=bias)
         self.act_layer = act_layer()
         # the one-pass kernels hard-wire tanh-GELU (mlp.py:65-70 with the released act_layer); any other activation runs
         # the plain PyTorch expression in eval and in training alike
@@ -206,23 +254,25 @@ class CrossAttentionFusion(nn.Module):
     def __init__(self, dim, num_heads=8, qkv_bias=True):
         super().__init__()
         self.num_heads, self.head_dim = num_heads, dim // 2 // num_heads
-        self.qkv1 = nn.Linear(dim // 2, dim // 2 * 3, bias=qkv_bias)
-        self.qkv2 = nn.Linear(dim // 2, dim // 2 * 3, bias=qkv_bias)
-        self.proj = nn.Linear(dim, dim)
+        self.qkv1 = Linear(dim // 2, dim // 2 * 3, bias=qkv_bias)
+        self.qkv2 = Linear(dim // 2, dim // 2 * 3, bias=qkv_bias)
+        self.proj = Linear(dim, dim)
 
     def forward(self, x1, x2):
         B, N, C = x1.shape
-        q1, k1, v1 = self.qkv1(x1).view(B, N, 3, self.num_heads, self.head_dim).permute(2, 0, 3, 1, 4).unbind(0)
-        q2, k2, v2 = self.qkv2(x2).view(B, N, 3, self.num_heads, self.head_dim).permute(2, 0, 3, 1, 4).unbind(0)
+        q1, k1, v1 = _split_qkv(self.qkv1(x1), self.num_heads)
+        q2, k2, v2 = _split_qkv(self.qkv2(x2), self.num_heads)
         if attention_supported(q1, k2, v2) and attention_supported(q2, k1, v1):
             # both cross attentions write their halves of the (B, N, 2C) input of `proj` directly: no transpose, no cat
             both = torch.empty((B, N, 2 * C), device=x1.device, dtype=q1.dtype)
             attention(q1, k2, v2, out=both[:, :, :C].view(B, N, self.num_heads, self.head_dim))
             attention(q2, k1, v1, out=both[:, :, C:].view(B, N, self.num_heads, self.head_dim))
             return self.proj(both)
-        x12 = F.scaled_dot_product_attention(q1, k2, v2).transpose(1, 2).reshape(B, N, C)
-        x21 = F.scaled_dot_product_attention(q2, k1, v1).transpose(1, 2).reshape(B, N, C)
-        return self.proj(torch.cat((x12, x21), dim=-1))
+        # cat((x12, x21), -1) of the head-merged outputs == the two (B, N, H, D) outputs stacked along the head axis: one
+        # pass instead of two transpose copies and a cat
+        o12 = F.scaled_dot_product_attention(q1, k2, v2).transpose(1, 2)
+        o21 = F.scaled_dot_product_attention(q2, k1, v1).transpose(1, 2)
+        return self.proj(torch.cat((o12, o21), dim=2).view(B, N, 2 * C))
 
 
 def _block_order(mixer, order, inv, device):
@@ -252,7 +302,7 @@ class DiMBlockRaw(nn.Module):
         self.reverse, self.transpose = reverse, transpose
         self.mixer = mixer_cls(dim)
         self.norm = nn.Identity()
-        self.adaLN_modulation = nn.Sequential(nn.SiLU(), nn.Linear(c_dim, 3 * dim, bias=True))
+        self.adaLN_modulation = nn.Sequential(nn.SiLU(), Linear(c_dim, 3 * dim, bias=True))
         order = so.implicit_order(grid, transpose, reverse) if (reverse or transpose) else None
         self.register_buffer("_order", _order_buffer(order) if order is not None else None, persistent=False)
         self.register_buffer("_inv", _order_buffer(so.reverse_permut_np(order)) if order is not None else None,
@@ -260,12 +310,13 @@ class DiMBlockRaw(nn.Module):
 
     def forward(self, x, c):
         shift, scale, gate = self.adaLN_modulation(c).chunk(3, dim=1)
-        if _fused_ok(x):
+        if _fused_ok(x) or _train_fused_ok(x, shift, scale, gate):
             # the scan order (implicit transpose / flip, or the mixer's zigma / sweep / jpeg table) rides on the row index
-            # of the two glue kernels: no permuted copy, no extra pass, and the mixer runs gather-free
+            # of the two glue kernels -- and of their backward kernels when the pass is recorded: no permuted copy, no
+            # extra pass, and the mixer runs gather-free
             order, inv = _block_order(self.mixer, self._order, self._inv, x.device)
-            m = self.mixer(_mod(x, shift, scale, order), c, pre_ordered=True)
-            return _gated(x, gate, m, inv, feeds_gemm=True)
+            m = self.mixer(_mod(x, shift, scale, order, inv), c, pre_ordered=True)
+            return _gated(x, gate, m, inv, order, feeds_gemm=True)
         return x + gate.unsqueeze(1) * self.mixer(modulate(x, shift, scale), c, order=self._order)
 
 
@@ -278,7 +329,7 @@ class WaveDiMBlock(nn.Module):
             raise NotImplementedError("only the released 2-level wavelet packet is implemented")
         self.mixer = mixer_cls(dim)
         self.norm = nn.Identity()
-        self.adaLN_modulation = nn.Sequential(nn.SiLU(), nn.Linear(c_dim, 3 * dim, bias=True))
+        self.adaLN_modulation = nn.Sequential(nn.SiLU(), Linear(c_dim, 3 * dim, bias=True))
         # Haar filter buffers exist in reference checkpoints (wavelet_layer.py:71-89,95-114); kept so strict loading works
         s = 0.5
         self.dwt = nn.Module()
@@ -292,9 +343,9 @@ class WaveDiMBlock(nn.Module):
     def forward(self, x, c):
         h = wavelet_packet(x, self._pos)                                 # _dwt_fast + local_scan
         shift, scale, gate = self.adaLN_modulation(c).chunk(3, dim=1)
-        if _fused_ok(h):
+        if _fused_ok(h) or _train_fused_ok(h, shift, scale, gate):
             order, inv = _block_order(self.mixer, None, None, h.device)      # the mixer's own table, if its scan type has one
-            h = _gated(h, gate, self.mixer(_mod(h, shift, scale, order), c, pre_ordered=True), inv, feeds_gemm=True)
+            h = _gated(h, gate, self.mixer(_mod(h, shift, scale, order, inv), c, pre_ordered=True), inv, order, feeds_gemm=True)
         else:
             h = _gated(h, gate, self.mixer(_mod(h, shift, scale), c), feeds_gemm=True)
         return wavelet_packet_inverse(h, self._pos)                      # local_reverse + _idwt_fast
@@ -308,7 +359,7 @@ class DiMBlockCombined(nn.Module):
         self.freq_mamba = WaveDiMBlock(dim // 2, mixer_cls, c_dim=dim, grid=grid, column_first=reverse)
         self.proj = CrossAttentionFusion(dim, num_heads=8, qkv_bias=True)
         self.norm_2 = RMSNorm(dim, eps=eps)
-        self.adaLN_modulation = nn.Sequential(nn.SiLU(), nn.Linear(dim, 3 * dim, bias=True))
+        self.adaLN_modulation = nn.Sequential(nn.SiLU(), Linear(dim, 3 * dim, bias=True))
         self.mlp = GatedMLP(dim, int(dim * 4), act_layer=lambda: nn.GELU(approximate="tanh"))
 
     def forward(self, hidden_states, residual, c):
@@ -328,7 +379,7 @@ class DiTBlock(nn.Module):
         self.attn = Attention(hidden_size, num_heads=num_heads, qkv_bias=True)
         self.norm2 = nn.LayerNorm(hidden_size, elementwise_affine=False, eps=1e-6)
         self.mlp = GatedMLP(hidden_size, int(hidden_size * 4), act_layer=lambda: nn.GELU(approximate="tanh"))
-        self.adaLN_modulation = nn.Sequential(nn.SiLU(), nn.Linear(hidden_size, 6 * hidden_size, bias=True))
+        self.adaLN_modulation = nn.Sequential(nn.SiLU(), Linear(hidden_size, 6 * hidden_size, bias=True))
 
     def forward(self, x, c):
         s1, sc1, g1, s2, sc2, g2 = self.adaLN_modulation(c).chunk(6, dim=1)
@@ -340,8 +391,8 @@ class FinalLayer(nn.Module):
     def __init__(self, hidden_size, patch_size, out_channels):
         super().__init__()
         self.norm_final = nn.LayerNorm(hidden_size, elementwise_affine=False, eps=1e-6)
-        self.linear = nn.Linear(hidden_size, patch_size * patch_size * out_channels, bias=True)
-        self.adaLN_modulation = nn.Sequential(nn.SiLU(), nn.Linear(hidden_size, 2 * hidden_size, bias=True))
+        self.linear = Linear(hidden_size, patch_size * patch_size * out_channels, bias=True)
+        self.adaLN_modulation = nn.Sequential(nn.SiLU(), Linear(hidden_size, 2 * hidden_size, bias=True))
 
     def forward(self, x, c):
         shift, scale = self.adaLN_modulation(c).chunk(2, dim=1)

@@ -11,7 +11,7 @@ import os
 import torch
 import torch.nn.functional as F
 
-from . import causal_conv1d_cuda, selective_scan_cuda
+from . import amp, causal_conv1d_cuda, selective_scan_cuda
 
 
 def fused_xproj_enabled():
@@ -85,10 +85,15 @@ def _rows_times_wt(t_bdl, weight):
 
 
 def _autocast_weights(*ws):
+    """Weights in the autocast dtype: the attached bf16 shadow when there is one (amp.Bf16Shadows), else a cast."""
     if not torch.is_autocast_enabled():
         return ws
     dt = torch.get_autocast_dtype("cuda")
-    return tuple(w.to(dt) if w is not None else None for w in ws)
+    out = []
+    for w in ws:
+        sh = amp.shadow_of(w)
+        out.append(sh if sh is not None else (w.to(dt) if w is not None else None))
+    return tuple(out)
 
 
 class MambaInnerFn(torch.autograd.Function):
@@ -111,6 +116,8 @@ class MambaInnerFn(torch.autograd.Function):
         L = xz.shape[-1]
         rank = delta_proj_weight.shape[1]
         N = A.shape[-1]
+        # dtypes of the master weights: backward writes their gradients in these directly from the GEMMs
+        ctx.w_dtypes = tuple(w.dtype if w is not None else None for w in (x_proj_weight, delta_proj_weight, out_proj_weight))
         x_proj_weight, delta_proj_weight, out_proj_weight, out_proj_bias = _autocast_weights(
             x_proj_weight, delta_proj_weight, out_proj_weight, out_proj_bias)
         xz = _last_contig(xz)
@@ -181,7 +188,7 @@ class MambaInnerFn(torch.autograd.Function):
             conv_out, delta, A, Bm, Cm, D, z, delta_bias, dout_y, x_ckpt, out, dz, ctx.delta_softplus, True)
         dout_proj_weight = dout_proj_bias = None
         if ctx.has_out_proj:
-            dout_proj_weight = dout2 @ out_z.transpose(1, 2).reshape(R * L, Dm)
+            dout_proj_weight = amp.mm_wgrad(dout2, out_z.transpose(1, 2).reshape(R * L, Dm), ctx.w_dtypes[2])
             dout_proj_bias = dout2.sum(dim=1) if ctx.out_bias else None
         dx_dbl = torch.empty((R * L, rank + 2 * N), device=xz.device, dtype=dt2d.dtype)
         dBf = dB.squeeze(1).transpose(1, 2).reshape(R * L, N)
@@ -191,12 +198,17 @@ class MambaInnerFn(torch.autograd.Function):
         dB_proj_bias = dBf.sum(0) if ctx.B_bias else None
         dC_proj_bias = dCf.sum(0) if ctx.C_bias else None
         ddelta2 = ddelta.transpose(0, 1).reshape(Dm, R * L)
-        ddelta_proj_weight = ddelta2 @ dt2d.t()
+        ddelta_proj_weight = amp.mm_wgrad(ddelta2, dt2d.t(), ctx.w_dtypes[1])
         dx_dbl[:, :rank] = ddelta2.t() @ delta_proj_weight
         conv_flat = conv_out.transpose(1, 2).reshape(R * L, Dm)
-        dx_proj_weight = dx_dbl.t() @ conv_flat
-        dconv_out = dconv_out + (dx_dbl @ x_proj_weight).view(R, L, Dm).transpose(1, 2)
-        dconv_out = _last_contig(dconv_out)
+        dx_proj_weight = amp.mm_wgrad(dx_dbl.t(), conv_flat, ctx.w_dtypes[0])
+        # dconv_out (R, Dm, L) += x_proj_weight^T (Dm, E) @ dx_dbl^T (E, L) per batch row: the GEMM accumulates into the scan's
+        # du in its own layout (one pass; a plain `dx_dbl @ x_proj_weight` would come out token-major and need a strided add)
+        xw = x_proj_weight if x_proj_weight.dtype == dx_dbl.dtype else x_proj_weight.to(dx_dbl.dtype)
+        if dconv_out.dtype == dx_dbl.dtype and dconv_out.is_contiguous():
+            dconv_out.baddbmm_(xw.t().unsqueeze(0).expand(R, -1, -1), dx_dbl.view(R, L, -1).transpose(1, 2))
+        else:
+            dconv_out = _last_contig(dconv_out + (dx_dbl @ xw).view(R, L, Dm).transpose(1, 2))
         dx, dconv_w, dconv_b = causal_conv1d_cuda.causal_conv1d_bwd(x, conv_w, conv1d_bias, dconv_out, dx, True)
         return (dxz, dconv_w.unsqueeze(1), dconv_b if conv1d_bias is not None else None, dx_proj_weight,
                 ddelta_proj_weight, dout_proj_weight, dout_proj_bias, dA, None, None, dD,

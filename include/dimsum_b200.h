@@ -335,7 +335,7 @@ int dimsum_cfg_euler_step(const dimsum_cfg_euler_params *p, void *stream);
 /* ---- backward pieces of the glue (training) ------------------------------------------------ */
 /* Column sums over the tokens of each batch row, the reductions autograd needs for adaLN modulate / gated residual
  * (d shift = sum_l g, d scale = sum_l g x, d gate = sum_l g m; reference: autograd through models_dim.py:34-35, 1509-1512):
- *     sum_g[b, c] = sum_l g[b, l, c]            sum_gx[b, c] = sum_l g[b, l, c] * x[b, l, c]
+ *     sum_g[b, c] = sum_l g[b, l, c]            sum_gx[b, c] = sum_l g[b, l, c] * x[b, x_idx[l], c]
  * g, x: (batch, seqlen, channels) with channel stride 1, any of the three dtypes; either output may be NULL (x may be NULL
  * when sum_gx is); outputs (batch, channels) in out_dtype with row stride out_row_stride.  channels % 4 == 0.
  */
@@ -345,6 +345,7 @@ typedef struct {
     int64_t g_batch_stride, g_token_stride, x_batch_stride, x_token_stride, out_row_stride;
     const void *g, *x;
     void *sum_g, *sum_gx;
+    const int32_t *x_idx;      /* optional (seqlen,) token table: x is read at row x_idx[l] (g at row l); NULL = identity */
 } dimsum_colsum_params;
 
 int dimsum_token_colsum(const dimsum_colsum_params *p, void *stream);

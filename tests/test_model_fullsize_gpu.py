@@ -112,9 +112,12 @@ def _toy(name="toy256"):
     return raw, sd
 
 
-def test_bf16_autocast_forward_and_backward_match_oracle_under_autocast():
+@pytest.mark.parametrize("mode", ["bf16", "bf16_shadows", "fp32"])
+def test_recorded_forward_and_backward_match_oracle(mode):
     """configs[4] is a bf16-autocast config: the recorded (training) forward and ALL parameter gradients of the toy reference
-    model under bf16 autocast vs autograd through the oracle under the same autocast, on the same device."""
+    model vs autograd through the oracle on the same device -- under bf16 autocast (plain, and with the bf16 weight shadows of
+    dimsum_b200/amp.py) at the bf16 tolerance, and in strict fp32 at 1e-4 (orders folded into the glue kernels' backward)."""
+    from dimsum_b200 import amp
     from dimsum_b200.models_dim import DiM
     from oracle import ref_model
     raw, sd = _toy()
@@ -126,18 +129,30 @@ def test_bf16_autocast_forward_and_backward_match_oracle_under_autocast():
     g = torch.Generator().manual_seed(5)
     dout = torch.randn(raw["out/plain"].shape, generator=g).cuda()
     m.y_embedder.dropout_prob = 0.0                                           # deterministic labels
-    with torch.autocast("cuda", dtype=torch.bfloat16):
-        out = m(x, t, y)
-    (out.float() * dout).sum().backward()
-    ours = {n: p.grad for n, p in m.named_parameters() if p.grad is not None}
+    low = mode != "fp32"
+    shadows = amp.Bf16Shadows(m) if mode == "bf16_shadows" else None
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = low
+    try:
+        ctx = lambda: torch.autocast("cuda", dtype=torch.bfloat16, enabled=low)
+        with ctx():
+            out = m(x, t, y)
+        (out.float() * dout).sum().backward()
+        ours = {n: p.grad for n, p in m.named_parameters() if p.grad is not None}
+        assert all(gr.dtype == torch.float32 for gr in ours.values())
 
-    leaves = {k: v.cuda().clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
-    with torch.autocast("cuda", dtype=torch.bfloat16):
-        want = ref_model.dim_forward_oracle(leaves, x, t, y)
-    (want.float() * dout).sum().backward()
+        leaves = {k: v.cuda().clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+        with ctx():
+            want = ref_model.dim_forward_oracle(leaves, x, t, y)
+        (want.float() * dout).sum().backward()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+        if shadows is not None:
+            shadows.detach()
+    tol = 2e-2 if low else 1e-4
     e = rel_err(out, want)
-    print(f"bf16 autocast forward rel err vs oracle under autocast: {e:.3e}")
-    assert e <= 2e-2, e
+    print(f"{mode} recorded forward rel err vs oracle: {e:.3e}")
+    assert e <= (tol if low else 5e-5), e
     worst = ("", 0.0)
     num = den = 0.0
     for n, gr in ours.items():
@@ -150,7 +165,7 @@ def test_bf16_autocast_forward_and_backward_match_oracle_under_autocast():
         if err > worst[1]:
             worst = (n, err)
     total = (num / den) ** 0.5
-    print(f"bf16 autocast gradients: global l2 rel err {total:.3e}; worst per-parameter max-norm rel err {worst[1]:.3e} ({worst[0]})")
-    assert total <= 2e-2, total
+    print(f"{mode} gradients: global l2 rel err {total:.3e}; worst per-parameter max-norm rel err {worst[1]:.3e} ({worst[0]})")
+    assert total <= tol, total
     # every trainable parameter that the oracle gives a gradient also got one here
     assert all(n in ours for n, v in leaves.items() if v.grad is not None and "cond_proj" not in n)

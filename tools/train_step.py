@@ -39,7 +39,8 @@ class TrainStep:
     replays) forward + backward (+ DDP all-reduce) + clip + AdamW; returns the loss tensor."""
 
     def __init__(self, dev, rank, world, batch=32, dtype="bf16", model_name="DiM-L/2", depth=None, use_graph=True, res=32,
-                 bucket_mb=100):
+                 bucket_mb=100, shadows=True):
+        from dimsum_b200 import amp
         from dimsum_b200.models_dim import DiM, DiM_models
         self.dev, self.rank, self.world, self.batch, self.res = dev, rank, world, batch, res
         torch.manual_seed(0)
@@ -52,6 +53,10 @@ class TrainStep:
                 if "adaLN_modulation" in n or n.startswith("final_layer.linear"):
                     p.normal_(0, 0.02)
         self.model = model.to(dev).train()
+        # bf16 copies of the GEMM weights, refreshed by one multi-tensor copy after the optimizer step, instead of autocast's
+        # per-weight casts every forward and backward (dimsum_b200/amp.py); DIMSUM_BF16_SHADOWS=0 / shadows=False: plain autocast
+        use_shadows = shadows and dtype == "bf16" and os.environ.get("DIMSUM_BF16_SHADOWS", "1") != "0"
+        self.shadows = amp.Bf16Shadows(self.model) if use_shadows else None
         self.amp = torch.autocast("cuda", dtype=torch.bfloat16, enabled=dtype == "bf16")
         self.g = torch.Generator(device=dev).manual_seed(rank)
         self.use_graph = use_graph
@@ -93,6 +98,8 @@ class TrainStep:
         loss.backward()
         torch.nn.utils.clip_grad_norm_(self.model.parameters(), 1.0)
         self.opt.step()
+        if self.shadows is not None:
+            self.shadows.refresh()
         return loss
 
     def step(self, batch=None):
@@ -149,11 +156,17 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     if args.profile and rank == 0:
         from torch.profiler import ProfilerActivity, profile
-        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True, with_stack=True) as prof:
             ts.step()
             torch.cuda.synchronize()
         with open(args.profile, "w") as f:
             f.write(prof.key_averages().table(sort_by="self_cuda_time_total", row_limit=70, max_name_column_width=90))
+        with open(args.profile + ".shapes", "w") as f:      # which call sites the framework glue (copies, cats, sums) comes from
+            f.write(prof.key_averages(group_by_input_shape=True).table(sort_by="self_cuda_time_total", row_limit=80,
+                                                                        max_name_column_width=60, max_shapes_column_width=90))
+        with open(args.profile + ".stacks", "w") as f:
+            f.write(prof.key_averages(group_by_stack_n=6).table(sort_by="self_cuda_time_total", row_limit=60,
+                                                                 max_name_column_width=50, max_src_column_width=110))
     if rank == 0:
         print(json.dumps({"metric": "DiMSUM-L/2 train latents/s", "value": args.batch * world / (ms.item() * 1e-3),
                           "ms_per_step": ms.item(), "n_gpus": world, "per_gpu_batch": args.batch, "dtype": args.dtype,
