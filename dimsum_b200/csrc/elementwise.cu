@@ -31,6 +31,38 @@ DEV void st8(void *base, int dtype, int64_t idx, const float (&v)[8]) {
     }
 }
 
+// 8 consecutive channels as raw bits (32 B fp32 / 16 B 16-bit) and their conversion: see ld_raw4 below for why they are apart
+struct Raw8 { uint4 a, b; };
+DEV Raw8 ld_raw8(const void *base, int dtype, int64_t idx) {
+    Raw8 r;
+    r.b = make_uint4(0u, 0u, 0u, 0u);
+    if (dtype == DIMSUM_F32) {
+        const uint4 *p = reinterpret_cast<const uint4 *>(reinterpret_cast<const float *>(base) + idx);
+        r.a = p[0]; r.b = p[1];
+    } else {
+        r.a = *reinterpret_cast<const uint4 *>(reinterpret_cast<const uint16_t *>(base) + idx);
+    }
+    return r;
+}
+DEV void cvt_raw8(const Raw8 &r, int dtype, float (&v)[8]) {
+    if (dtype == DIMSUM_F32) {
+        v[0] = __uint_as_float(r.a.x); v[1] = __uint_as_float(r.a.y); v[2] = __uint_as_float(r.a.z); v[3] = __uint_as_float(r.a.w);
+        v[4] = __uint_as_float(r.b.x); v[5] = __uint_as_float(r.b.y); v[6] = __uint_as_float(r.b.z); v[7] = __uint_as_float(r.b.w);
+    } else {
+        const uint32_t w[4] = {r.a.x, r.a.y, r.a.z, r.a.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (dtype == DIMSUM_BF16) {
+                v[2 * i] = __uint_as_float(w[i] << 16);
+                v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+            } else {
+                const float2 f = __half22float2(reinterpret_cast<const __half2 &>(w[i]));
+                v[2 * i] = f.x; v[2 * i + 1] = f.y;
+            }
+        }
+    }
+}
+
 // one thread = 8 consecutive channels of one token; all loads are issued before the arithmetic
 template <bool kGate>
 __global__ void __launch_bounds__(256) rowwise_kernel(const dimsum_rowwise_params p) {
@@ -44,19 +76,17 @@ __global__ void __launch_bounds__(256) rowwise_kernel(const dimsum_rowwise_param
     const int src_l = p.idx != nullptr ? p.idx[l] : l;
     const int c0 = v * 8;
     float a[8], q[8], r[8], o[8];
-    if (!kGate) {
-        ld8(p.x, (int)p.x_dtype, b * p.x_batch_stride + (int64_t)src_l * p.x_token_stride + c0, a);
-        ld8(p.shift, (int)p.aux_dtype, b * p.vec_row_stride + c0, q);
-        ld8(p.scale, (int)p.aux_dtype, b * p.vec_row_stride + c0, r);
+    // the three loads go out back to back as raw bits; the conversions (their first use) come after the last one is issued
+    const int x_dt = (int)p.x_dtype, aux_dt = (int)p.aux_dtype;
+    const Raw8 ra = ld_raw8(p.x, x_dt, b * p.x_batch_stride + (int64_t)(kGate ? l : src_l) * p.x_token_stride + c0);
+    const Raw8 rq = kGate ? ld_raw8(p.m, aux_dt, b * p.m_batch_stride + (int64_t)src_l * p.m_token_stride + c0)
+                          : ld_raw8(p.shift, aux_dt, b * p.vec_row_stride + c0);
+    const Raw8 rr = ld_raw8(kGate ? p.gate : p.scale, aux_dt, b * p.vec_row_stride + c0);
+    cvt_raw8(ra, x_dt, a);
+    cvt_raw8(rq, aux_dt, q);
+    cvt_raw8(rr, aux_dt, r);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = fmaf(a[i], 1.f + r[i], q[i]);
-    } else {
-        ld8(p.x, (int)p.x_dtype, b * p.x_batch_stride + (int64_t)l * p.x_token_stride + c0, a);
-        ld8(p.m, (int)p.aux_dtype, b * p.m_batch_stride + (int64_t)src_l * p.m_token_stride + c0, q);
-        ld8(p.gate, (int)p.aux_dtype, b * p.vec_row_stride + c0, r);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = fmaf(r[i], q[i], a[i]);
-    }
+    for (int i = 0; i < 8; ++i) o[i] = kGate ? fmaf(r[i], q[i], a[i]) : fmaf(a[i], 1.f + r[i], q[i]);
     st8(p.dst, (int)p.dst_dtype, b * p.dst_batch_stride + (int64_t)l * p.dst_token_stride + c0, o);
 }
 
@@ -79,6 +109,31 @@ DEV void st_rt(void *base, int dtype, int64_t idx, const float (&v)[VEC]) {
         if (dtype == DIMSUM_F32) Io<float>::st4(reinterpret_cast<float *>(base) + idx + i, q);
         else if (dtype == DIMSUM_BF16) Io<__nv_bfloat16>::st4(reinterpret_cast<__nv_bfloat16 *>(base) + idx + i, q);
         else Io<__half>::st4(reinterpret_cast<__half *>(base) + idx + i, q);
+    }
+}
+
+// Four consecutive channels as RAW bits (16 B for fp32, 8 B for the 16-bit types) and their conversion, kept apart on purpose:
+// a converting load is used the moment it is issued, and an in-order warp then waits for it before it issues the next one.
+// Kernels that depend on many loads in flight issue all their ld_raw4 first and convert afterwards.
+DEV uint4 ld_raw4(const void *base, int dtype, int64_t idx) {
+    uint4 r = make_uint4(0u, 0u, 0u, 0u);
+    if (dtype == DIMSUM_F32) {
+        r = *reinterpret_cast<const uint4 *>(reinterpret_cast<const float *>(base) + idx);
+    } else {
+        const uint2 h = *reinterpret_cast<const uint2 *>(reinterpret_cast<const uint16_t *>(base) + idx);
+        r.x = h.x; r.y = h.y;
+    }
+    return r;
+}
+DEV void cvt_raw4(const uint4 r, int dtype, float (&v)[4]) {
+    if (dtype == DIMSUM_F32) {
+        v[0] = __uint_as_float(r.x); v[1] = __uint_as_float(r.y); v[2] = __uint_as_float(r.z); v[3] = __uint_as_float(r.w);
+    } else if (dtype == DIMSUM_BF16) {
+        v[0] = __uint_as_float(r.x << 16); v[1] = __uint_as_float(r.x & 0xffff0000u);
+        v[2] = __uint_as_float(r.y << 16); v[3] = __uint_as_float(r.y & 0xffff0000u);
+    } else {
+        const float2 f0 = __half22float2(reinterpret_cast<const __half2 &>(r.x)), f1 = __half22float2(reinterpret_cast<const __half2 &>(r.y));
+        v[0] = f0.x; v[1] = f0.y; v[2] = f1.x; v[3] = f1.y;
     }
 }
 
@@ -262,43 +317,71 @@ __global__ void __launch_bounds__(256) cfg_euler_kernel(const dimsum_cfg_euler_p
     }
 }
 
-// column sums over the tokens of a batch row: CTA = (128 channels, batch row); 8 warps stride over the tokens, a lane
-// owns 4 consecutive channels, partial sums meet in shared memory
-__global__ void __launch_bounds__(256) colsum_kernel(const dimsum_colsum_params p) {
-    __shared__ float red[2][8][128];
+// column sums over the tokens of a batch row: CTA = (128 channels, batch row); kColsumWarps warps stride over the tokens
+// with kColsumUnroll rows of loads in flight per lane (a (32, 256, 512) bf16 gradient is only 128 CTAs: the bytes in flight
+// come from the unroll, not from the grid), a lane owns 4 consecutive channels, partial sums meet in shared memory
+constexpr int kColsumWarps = 16;
+template <bool kWantX>
+__global__ void __launch_bounds__(kColsumWarps * 32) colsum_kernel(const dimsum_colsum_params p) {
+    constexpr int kColsumUnroll = kWantX ? 8 : 16;          // 16 loads in flight per lane either way
+    __shared__ float red[2][kColsumWarps][128];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c0 = blockIdx.x * 128 + lane * 4;
     const int64_t b = blockIdx.y;
-    const bool want_x = p.sum_gx != nullptr;
+    constexpr bool want_x = kWantX;
+    const int g_dt = (int)p.g_dtype, x_dt = (int)p.x_dtype;
     float sg[4] = {0.f, 0.f, 0.f, 0.f}, sx[4] = {0.f, 0.f, 0.f, 0.f};
     if (c0 < p.channels) {
-        for (int l = warp; l < p.seqlen; l += 8) {
-            float g[4], x[4];
-            ld_rt<4>(p.g, (int)p.g_dtype, b * p.g_batch_stride + (int64_t)l * p.g_token_stride + c0, g);
-            if (want_x) {
-                const int64_t lx = p.x_idx != nullptr ? (int64_t)__ldg(p.x_idx + l) : (int64_t)l;
-                ld_rt<4>(p.x, (int)p.x_dtype, b * p.x_batch_stride + lx * p.x_token_stride + c0, x);
-            }
+        const int64_t gbase = b * p.g_batch_stride + c0, xbase = b * p.x_batch_stride + c0;
+        const int last = (int)p.seqlen - 1;
+        for (int l0 = warp; l0 < p.seqlen; l0 += kColsumWarps * kColsumUnroll) {
+            // rows past the end re-read the last row (unconditional loads: nothing for the later ones to queue behind) and
+            // are masked out of the sums
+            int lx[kColsumUnroll];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                sg[i] += g[i];
-                if (want_x) sx[i] = fmaf(g[i], x[i], sx[i]);
+            for (int j = 0; j < kColsumUnroll; ++j) {
+                const int l = min(l0 + j * kColsumWarps, last);
+                lx[j] = (want_x && p.x_idx != nullptr) ? __ldg(p.x_idx + l) : l;
+            }
+            uint4 graw[kColsumUnroll], xraw[kColsumUnroll];
+#pragma unroll
+            for (int j = 0; j < kColsumUnroll; ++j)
+                graw[j] = ld_raw4(p.g, g_dt, gbase + (int64_t)min(l0 + j * kColsumWarps, last) * p.g_token_stride);
+            if (want_x) {
+#pragma unroll
+                for (int j = 0; j < kColsumUnroll; ++j) xraw[j] = ld_raw4(p.x, x_dt, xbase + (int64_t)lx[j] * p.x_token_stride);
+            }
+            __syncwarp();           // scheduling fence: keeps ptxas from sinking the loads between the sums to save registers
+#pragma unroll
+            for (int j = 0; j < kColsumUnroll; ++j) {
+                const float keep = (l0 + j * kColsumWarps <= last) ? 1.f : 0.f;
+                float g[4], x[4];
+                cvt_raw4(graw[j], g_dt, g);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { g[i] *= keep; sg[i] += g[i]; }
+                if (want_x) {
+                    cvt_raw4(xraw[j], x_dt, x);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) sx[i] = fmaf(g[i], x[i], sx[i]);
+                }
             }
         }
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) { red[0][warp][lane * 4 + i] = sg[i]; red[1][warp][lane * 4 + i] = sx[i]; }
     __syncthreads();
-    const int which = threadIdx.x >> 7, c = threadIdx.x & 127;           // 256 threads: 2 outputs x 128 channels
-    void *dst = which ? p.sum_gx : p.sum_g;
-    if (dst != nullptr && blockIdx.x * 128 + c < p.channels) {
-        float t = 0.f;
+    if (threadIdx.x < 256) {                                             // 2 outputs x 128 channels
+        const int which = threadIdx.x >> 7, c = threadIdx.x & 127;
+        void *dst = which ? p.sum_gx : p.sum_g;
+        if (dst != nullptr && blockIdx.x * 128 + c < p.channels) {
+            float t = 0.f;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) t += red[which][w][c];
-        const int64_t o = b * p.out_row_stride + blockIdx.x * 128 + c;
-        if (p.out_dtype == DIMSUM_F32) reinterpret_cast<float *>(dst)[o] = t;
-        else if (p.out_dtype == DIMSUM_BF16) reinterpret_cast<__nv_bfloat16 *>(dst)[o] = __float2bfloat16_rn(t);
-        else reinterpret_cast<__half *>(dst)[o] = __float2half_rn(t);
+            for (int w = 0; w < kColsumWarps; ++w) t += red[which][w][c];
+            const int64_t o = b * p.out_row_stride + blockIdx.x * 128 + c;
+            if (p.out_dtype == DIMSUM_F32) reinterpret_cast<float *>(dst)[o] = t;
+            else if (p.out_dtype == DIMSUM_BF16) reinterpret_cast<__nv_bfloat16 *>(dst)[o] = __float2bfloat16_rn(t);
+            else reinterpret_cast<__half *>(dst)[o] = __float2half_rn(t);
+        }
     }
 }
 
@@ -338,35 +421,42 @@ __global__ void __launch_bounds__(256) gelu_mul_bwd_kernel(const dimsum_gelu_mul
 
 // RMSNorm backward: one warp per row (the fp32 row h lives in registers), a CTA's 8 warps walk rows blockIdx.x*8+warp,
 // += gridDim.x*8, ... and keep their dweight contributions in registers; one shared-memory reduction per CTA at the end
+// (the weight is re-read through L1 for every row rather than kept in 32 more registers: at 1024 channels that is the
+// difference between one and two resident CTAs per SM, and the kernel is bound by rows in flight)
 template <int kMaxIter>
-__global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const dimsum_rmsnorm_bwd_params p) {
+__global__ void __launch_bounds__(256, 2) rmsnorm_bwd_kernel(const dimsum_rmsnorm_bwd_params p) {
     __shared__ float red[8][32 * kMaxIter * 4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nvec = (int)(p.channels / 4);
     const float *w = reinterpret_cast<const float *>(p.weight);
-    float wv[kMaxIter][4], dw[kMaxIter][4];
+    float dw[kMaxIter][4];
 #pragma unroll
-    for (int it = 0; it < kMaxIter; ++it) {
-        const int v = lane + it * 32;
+    for (int it = 0; it < kMaxIter; ++it)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { dw[it][i] = 0.f; wv[it][i] = v < nvec ? w[v * 4 + i] : 0.f; }
-    }
+        for (int i = 0; i < 4; ++i) dw[it][i] = 0.f;
     const float inv_c = 1.f / (float)p.channels;
     for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < p.rows; row += (int64_t)gridDim.x * 8) {
         const float *h = reinterpret_cast<const float *>(p.h) + row * p.channels;
         float hv[kMaxIter][4], gv[kMaxIter][4];
         float ss = 0.f;
+        {
+            // every load of the row is issued before the first value is used (vectors past the end of a short row re-read
+            // the last one and are zeroed afterwards)
+            uint4 hraw[kMaxIter], graw[kMaxIter];
 #pragma unroll
-        for (int it = 0; it < kMaxIter; ++it) {
-            const int v = lane + it * 32;
-            if (v < nvec) {
-                Io<float>::ld4(h + v * 4, hv[it]);
-                ld_rt<4>(p.dy, (int)p.dy_dtype, row * p.dy_row_stride + v * 4, gv[it]);
+            for (int it = 0; it < kMaxIter; ++it) {
+                const int v = min(lane + it * 32, nvec - 1);
+                hraw[it] = *reinterpret_cast<const uint4 *>(h + v * 4);
+                graw[it] = ld_raw4(p.dy, (int)p.dy_dtype, row * p.dy_row_stride + v * 4);
+            }
+            __syncwarp();           // scheduling fence, as in colsum_kernel
 #pragma unroll
-                for (int i = 0; i < 4; ++i) ss = fmaf(hv[it][i], hv[it][i], ss);
-            } else {
+            for (int it = 0; it < kMaxIter; ++it) {
+                const float keep = (lane + it * 32 < nvec) ? 1.f : 0.f;
+                cvt_raw4(hraw[it], DIMSUM_F32, hv[it]);
+                cvt_raw4(graw[it], (int)p.dy_dtype, gv[it]);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) { hv[it][i] = 0.f; gv[it][i] = 0.f; }
+                for (int i = 0; i < 4; ++i) { hv[it][i] *= keep; gv[it][i] *= keep; ss = fmaf(hv[it][i], hv[it][i], ss); }
             }
         }
 #pragma unroll
@@ -375,11 +465,15 @@ __global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const dimsum_rmsnorm_b
         float c1 = 0.f;
 #pragma unroll
         for (int it = 0; it < kMaxIter; ++it) {
+            const int v = lane + it * 32;
+            float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (v < nvec) wv = __ldg(reinterpret_cast<const float4 *>(w) + v);
+            const float wr[4] = {wv.x, wv.y, wv.z, wv.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 hv[it][i] *= rstd;                                   // xhat
                 dw[it][i] = fmaf(gv[it][i], hv[it][i], dw[it][i]);
-                gv[it][i] *= wv[it][i];                              // weight * dy
+                gv[it][i] *= wr[i];                                  // weight * dy
                 c1 = fmaf(gv[it][i], hv[it][i], c1);
             }
         }
@@ -526,7 +620,9 @@ extern "C" int dimsum_token_colsum(const dimsum_colsum_params *p, void *stream_)
                        (p->x == nullptr || (aligned16(p->x) && p->x_batch_stride % 4 == 0 && p->x_token_stride % 4 == 0)),
                    DIMSUM_ERR_UNSUPPORTED, "token_colsum: rows must be 16-byte aligned and channels a multiple of 4");
     DIMSUM_REQUIRE(p->batch <= 65535, DIMSUM_ERR_UNSUPPORTED, "token_colsum: batch > 65535");
-    colsum_kernel<<<dim3((unsigned)((p->channels + 127) / 128), (unsigned)p->batch), 256, 0, stream>>>(*p);
+    const dim3 grid((unsigned)((p->channels + 127) / 128), (unsigned)p->batch);
+    if (p->sum_gx != nullptr) colsum_kernel<true><<<grid, kColsumWarps * 32, 0, stream>>>(*p);
+    else colsum_kernel<false><<<grid, kColsumWarps * 32, 0, stream>>>(*p);
     return check_launch("token_colsum");
 }
 
@@ -558,7 +654,7 @@ extern "C" int dimsum_add_rmsnorm_bwd(const dimsum_rmsnorm_bwd_params *p, void *
                    "add_rmsnorm_bwd: unknown dtype");
     DIMSUM_REQUIRE(p->channels % 4 == 0 && p->channels <= 1024, DIMSUM_ERR_UNSUPPORTED,
                    "add_rmsnorm_bwd: channels=%lld must be a multiple of 4 and at most 1024", (long long)p->channels);
-    DIMSUM_REQUIRE(aligned16(p->h) && aligned16(p->dy) && aligned16(p->dx) && p->dy_row_stride % 4 == 0 && p->dx_row_stride % 4 == 0 &&
+    DIMSUM_REQUIRE(aligned16(p->h) && aligned16(p->weight) && aligned16(p->dy) && aligned16(p->dx) && p->dy_row_stride % 4 == 0 && p->dx_row_stride % 4 == 0 &&
                        (p->dres_in == nullptr || aligned16(p->dres_in)) && (p->dres_out == nullptr || aligned16(p->dres_out)),
                    DIMSUM_ERR_UNSUPPORTED, "add_rmsnorm_bwd: rows must be 16-byte aligned");
     const unsigned blocks = (unsigned)p->n_partials;

@@ -175,7 +175,11 @@ class MambaInnerFn(torch.autograd.Function):
         N = A.shape[-1]
         x, z = xz.chunk(2, dim=1)
         dout = _last_contig(dout)
-        conv_out = causal_conv1d_cuda.causal_conv1d_fwd(x, conv_w, conv1d_bias, True)
+        # conv_out is recomputed channel-major over the WHOLE batch ((Dm, R, L) memory, like delta): the scan kernels take any
+        # batch / channel strides, and (Dm, R*L) views of conv_out and of the scan's du feed the x_proj GEMMs below without the
+        # transposing copies a (R, Dm, L) layout would need
+        conv_out = causal_conv1d_cuda.causal_conv1d_fwd_cond(
+            x, conv_w, conv1d_bias, True, torch.empty((Dm, R, L), device=xz.device, dtype=xz.dtype).transpose(0, 1))
         delta = (delta_proj_weight @ dt2d).view(Dm, R, L).transpose(0, 1)
         dxz = torch.empty_like(xz)
         dx, dz = dxz.chunk(2, dim=1)
@@ -200,13 +204,13 @@ class MambaInnerFn(torch.autograd.Function):
         ddelta2 = ddelta.transpose(0, 1).reshape(Dm, R * L)
         ddelta_proj_weight = amp.mm_wgrad(ddelta2, dt2d.t(), ctx.w_dtypes[1])
         dx_dbl[:, :rank] = ddelta2.t() @ delta_proj_weight
-        conv_flat = conv_out.transpose(1, 2).reshape(R * L, Dm)
-        dx_proj_weight = amp.mm_wgrad(dx_dbl.t(), conv_flat, ctx.w_dtypes[0])
-        # dconv_out (R, Dm, L) += x_proj_weight^T (Dm, E) @ dx_dbl^T (E, L) per batch row: the GEMM accumulates into the scan's
-        # du in its own layout (one pass; a plain `dx_dbl @ x_proj_weight` would come out token-major and need a strided add)
+        conv_t = conv_out.transpose(0, 1).reshape(Dm, R * L)                      # a view: conv_out is (Dm, R, L) memory
+        dx_proj_weight = amp.mm_wgrad(dx_dbl.t(), conv_t.t(), ctx.w_dtypes[0])
+        # dconv_out += x_proj_weight^T (Dm, E) @ dx_dbl^T (E, R*L): the GEMM accumulates into the scan's du in its own layout
+        # (one pass; a plain `dx_dbl @ x_proj_weight` would come out token-major and need a strided add)
         xw = x_proj_weight if x_proj_weight.dtype == dx_dbl.dtype else x_proj_weight.to(dx_dbl.dtype)
-        if dconv_out.dtype == dx_dbl.dtype and dconv_out.is_contiguous():
-            dconv_out.baddbmm_(xw.t().unsqueeze(0).expand(R, -1, -1), dx_dbl.view(R, L, -1).transpose(1, 2))
+        if dconv_out.dtype == dx_dbl.dtype and dconv_out.stride() == (L, R * L, 1):     # du = empty_like(u): channel-major too
+            dconv_out.transpose(0, 1).view(Dm, R * L).addmm_(xw.t(), dx_dbl.t())
         else:
             dconv_out = _last_contig(dconv_out + (dx_dbl @ xw).view(R, L, Dm).transpose(1, 2))
         dx, dconv_w, dconv_b = causal_conv1d_cuda.causal_conv1d_bwd(x, conv_w, conv1d_bias, dconv_out, dx, True)
