@@ -351,7 +351,9 @@ __global__ void __launch_bounds__(kColsumWarps * 32) colsum_kernel(const dimsum_
 #pragma unroll
                 for (int j = 0; j < kColsumUnroll; ++j) xraw[j] = ld_raw4(p.x, x_dt, xbase + (int64_t)lx[j] * p.x_token_stride);
             }
-            __syncwarp();           // scheduling fence: keeps ptxas from sinking the loads between the sums to save registers
+            // scheduling fence: keeps ptxas from sinking the loads between the sums to save registers.  Only the lanes that
+            // own channels are here (channels % 128 != 0 leaves the others outside the branch), hence the active mask
+            __syncwarp(__activemask());
 #pragma unroll
             for (int j = 0; j < kColsumUnroll; ++j) {
                 const float keep = (l0 + j * kColsumWarps <= last) ? 1.f : 0.f;
@@ -449,7 +451,7 @@ __global__ void __launch_bounds__(256, 2) rmsnorm_bwd_kernel(const dimsum_rmsnor
                 hraw[it] = *reinterpret_cast<const uint4 *>(h + v * 4);
                 graw[it] = ld_raw4(p.dy, (int)p.dy_dtype, row * p.dy_row_stride + v * 4);
             }
-            __syncwarp();           // scheduling fence, as in colsum_kernel
+            __syncwarp(__activemask());           // scheduling fence, as in colsum_kernel (the row loop is warp-uniform)
 #pragma unroll
             for (int it = 0; it < kMaxIter; ++it) {
                 const float keep = (lane + it * 32 < nvec) ? 1.f : 0.f;
