@@ -149,22 +149,26 @@ def test_weight_shadows_reproduce_autocast():
         assert torch.equal(lin(x), F.linear(x, lin.weight, lin.bias))
 
 
-def test_train_step_with_shadows_tracks_plain_autocast():
-    """Three optimizer steps of a small DiM under bf16 autocast, with and without the weight shadows: same losses and weights
-    to bf16 accuracy (tools/train_step.py, eager)."""
+def test_train_step_with_shadows_and_fused_clip_tracks_plain_autocast():
+    """Three optimizer steps of a small DiM under bf16 autocast: plain autocast + clip_grad_norm_, against the weight shadows
+    and against the clip folded into the fused AdamW kernel -- same losses and weights to bf16 accuracy, and gradients that
+    end up clipped either way (tools/train_step.py, eager)."""
     import os, sys
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
     from train_step import TrainStep
     dev = torch.device("cuda", 0)
     runs = []
-    for shadows in (False, True):
-        ts = TrainStep(dev, 0, 1, batch=4, dtype="bf16", depth=4, use_graph=False, shadows=shadows)
+    for shadows, fuse_clip in ((False, False), (True, False), (True, True)):
+        ts = TrainStep(dev, 0, 1, batch=4, dtype="bf16", depth=4, use_graph=False, shadows=shadows, fuse_clip=fuse_clip)
         assert (ts.shadows is not None) == shadows
         batch = [b.clone() for b in ts.draw()]
-        losses = [float(ts.step(batch)) for _ in range(3)]
+        losses = [float(ts.step(batch).detach()) for _ in range(3)]
         w = torch.cat([p.detach().flatten()[:4096] for n, p in ts.model.named_parameters() if "cond_proj" not in n])
-        runs.append((losses, w, ts.missing_grads()))
-    (l0, w0, m0), (l1, w1, m1) = runs
-    assert m0 == [] and m1 == []
-    assert all(abs(a - b) <= 2e-2 * abs(a) for a, b in zip(l0, l1)), (l0, l1)
-    assert rel_err(w1, w0) <= 1e-3, rel_err(w1, w0)
+        gnorm = torch.nn.utils.get_total_norm([p.grad for p in ts.model.parameters() if p.grad is not None])
+        runs.append((losses, w, ts.missing_grads(), float(gnorm)))
+    (l0, w0, m0, g0) = runs[0]
+    for l1, w1, m1, g1 in runs[1:]:
+        assert m0 == [] and m1 == []
+        assert all(abs(a - b) <= 2e-2 * abs(a) for a, b in zip(l0, l1)), (l0, l1)
+        assert rel_err(w1, w0) <= 1e-3, rel_err(w1, w0)
+        assert g1 <= 1.0 + 1e-3 and abs(g1 - g0) <= 2e-2 * g0, (g0, g1)

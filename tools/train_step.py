@@ -39,7 +39,7 @@ class TrainStep:
     replays) forward + backward (+ DDP all-reduce) + clip + AdamW; returns the loss tensor."""
 
     def __init__(self, dev, rank, world, batch=32, dtype="bf16", model_name="DiM-L/2", depth=None, use_graph=True, res=32,
-                 bucket_mb=100, shadows=True):
+                 bucket_mb=100, shadows=True, fuse_clip=True):
         from dimsum_b200 import amp
         from dimsum_b200.models_dim import DiM, DiM_models
         self.dev, self.rank, self.world, self.batch, self.res = dev, rank, world, batch, res
@@ -57,6 +57,7 @@ class TrainStep:
         # per-weight casts every forward and backward (dimsum_b200/amp.py); DIMSUM_BF16_SHADOWS=0 / shadows=False: plain autocast
         use_shadows = shadows and dtype == "bf16" and os.environ.get("DIMSUM_BF16_SHADOWS", "1") != "0"
         self.shadows = amp.Bf16Shadows(self.model) if use_shadows else None
+        self.fuse_clip = fuse_clip and os.environ.get("DIMSUM_FUSED_CLIP", "1") != "0"
         self.amp = torch.autocast("cuda", dtype=torch.bfloat16, enabled=dtype == "bf16")
         self.g = torch.Generator(device=dev).manual_seed(rank)
         self.use_graph = use_graph
@@ -96,7 +97,15 @@ class TrainStep:
         loss = (out.float() - ut).square().mean()
         self.opt.zero_grad(set_to_none=True)
         loss.backward()
-        torch.nn.utils.clip_grad_norm_(self.model.parameters(), 1.0)
+        if self.fuse_clip:
+            # clip_grad_norm_(1.0) = every gradient times min(1, 1 / (norm + 1e-6)).  The fused AdamW kernel divides the
+            # gradients by `grad_scale` on the fly (the hook torch.amp.GradScaler uses) and stores them back, so the clip rides
+            # on the optimizer's own pass instead of a separate read-modify-write of all gradients
+            grads = [p.grad for p in self.model.parameters() if p.grad is not None]
+            total = torch.nn.utils.get_total_norm(grads, foreach=True)
+            self.opt.grad_scale = torch.clamp(total + 1e-6, min=1.0).float()
+        else:
+            torch.nn.utils.clip_grad_norm_(self.model.parameters(), 1.0)
         self.opt.step()
         if self.shadows is not None:
             self.shadows.refresh()
