@@ -22,8 +22,9 @@ def shadow_of(param):
     if param is None or not torch.is_autocast_enabled():
         return None
     sh = getattr(param, "_dimsum_bf16", None)
-    if sh is None or torch.get_autocast_dtype("cuda") != sh.dtype or sh.device != param.device:
-        return None
+    if (sh is None or torch.get_autocast_dtype("cuda") != sh.dtype or sh.device != param.device
+            or param.dtype != torch.float32 or sh.shape != param.shape):
+        return None                                   # the master was moved / recast / resized after the shadow was attached
     if param._dimsum_bf16_version != param._version:
         sh.copy_(param.detach())
         param._dimsum_bf16_version = param._version

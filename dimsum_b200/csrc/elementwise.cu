@@ -140,35 +140,67 @@ DEV void cvt_raw4(const uint4 r, int dtype, float (&v)[4]) {
 // residual add + RMSNorm / LayerNorm (+ adaLN modulate): one warp per row, the row lives in registers between the
 // passes (channels <= 32 lanes * 8 * VEC: 1024 fp32, 2048 16-bit)
 // kMaxIter = 16-byte vectors per lane (1, 2, 4 or 8): sized to the row so that no predicated-off iterations are issued
+// one 16-byte vector of T as raw bits -> Io<T>::kVec floats
+template <typename T>
+DEV void cvt_vec(const uint4 r, float (&v)[Io<T>::kVec]) {
+    if constexpr (Io<T>::kVec == 4) {
+        cvt_raw4(r, DIMSUM_F32, v);
+    } else {
+        Raw8 q;
+        q.a = r; q.b = r;
+        cvt_raw8(q, Io<T>::kDtype, v);
+    }
+}
+
 template <typename T, bool kLayerNorm, int kMaxIter>
 __global__ void __launch_bounds__(256) norm_kernel(const dimsum_norm_modulate_params p) {
-    constexpr int VEC = Io<T>::kVec;
+    constexpr int VEC = Io<T>::kVec, Q = VEC / 4;
     const int warp = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
-    if (warp >= p.rows) return;
+    if (warp >= p.rows) return;                         // warp-uniform: the fences below see all 32 lanes
     const int nvec = (int)(p.channels / VEC);
     const T *x = reinterpret_cast<const T *>(p.x) + (int64_t)warp * p.x_row_stride;
     const float *res = p.residual != nullptr ? reinterpret_cast<const float *>(p.residual) + (int64_t)warp * p.channels : nullptr;
     float *res_out = p.res_out != nullptr ? reinterpret_cast<float *>(p.res_out) + (int64_t)warp * p.channels : nullptr;
     float vals[kMaxIter][VEC];
     float ss = 0.f, sum = 0.f;
+    {
+        // every load of the row goes out before the first value is used (raw bits now, conversion / add after the fence):
+        // vectors past the end of a short row re-read the last one and are zeroed
+        uint4 xr[kMaxIter], rr[kMaxIter][Q];
 #pragma unroll
-    for (int it = 0; it < kMaxIter; ++it) {
-        const int v = lane + it * 32;
-        if (v < nvec) {
-            Io<T>::ldv(x + v * VEC, vals[it]);
+        for (int it = 0; it < kMaxIter; ++it) {
+            const int v = min(lane + it * 32, nvec - 1);
+            xr[it] = *reinterpret_cast<const uint4 *>(x + v * VEC);
             if (res != nullptr) {
 #pragma unroll
-                for (int i = 0; i < VEC; i += 4) {
-                    const float4 r = *reinterpret_cast<const float4 *>(res + v * VEC + i);
-                    vals[it][i] += r.x; vals[it][i + 1] += r.y; vals[it][i + 2] += r.z; vals[it][i + 3] += r.w;
+                for (int q = 0; q < Q; ++q) rr[it][q] = *reinterpret_cast<const uint4 *>(res + v * VEC + 4 * q);
+            }
+        }
+        __syncwarp(__activemask());                     // scheduling fence (see colsum_kernel)
+#pragma unroll
+        for (int it = 0; it < kMaxIter; ++it) {
+            const int v = lane + it * 32;
+            cvt_vec<T>(xr[it], vals[it]);
+            if (res != nullptr) {
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    float r[4];
+                    cvt_raw4(rr[it][q], DIMSUM_F32, r);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) vals[it][4 * q + i] += r[i];
                 }
             }
-            if (res_out != nullptr) {
+            if (v < nvec) {
+                if (res_out != nullptr) {
 #pragma unroll
-                for (int i = 0; i < VEC; i += 4)
-                    *reinterpret_cast<float4 *>(res_out + v * VEC + i) =
-                        make_float4(vals[it][i], vals[it][i + 1], vals[it][i + 2], vals[it][i + 3]);
+                    for (int i = 0; i < VEC; i += 4)
+                        *reinterpret_cast<float4 *>(res_out + v * VEC + i) =
+                            make_float4(vals[it][i], vals[it][i + 1], vals[it][i + 2], vals[it][i + 3]);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) vals[it][i] = 0.f;
             }
 #pragma unroll
             for (int i = 0; i < VEC; ++i) {
@@ -176,6 +208,23 @@ __global__ void __launch_bounds__(256) norm_kernel(const dimsum_norm_modulate_pa
                 else ss = fmaf(vals[it][i], vals[it][i], ss);
             }
         }
+    }
+    // the adaLN rows (L2 hits, shared by the tokens of a batch row) are requested now, all of them, and used after the reductions
+    const bool mod = p.scale != nullptr;
+    const int aux_dt = (int)p.aux_dtype;
+    const int64_t mrow = mod ? (warp / p.rows_per_batch) * p.vec_row_stride : 0;
+    uint4 shr[kMaxIter][Q], scr[kMaxIter][Q];
+    if (mod) {
+#pragma unroll
+        for (int it = 0; it < kMaxIter; ++it) {
+            const int v = min(lane + it * 32, nvec - 1);
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                shr[it][q] = ld_raw4(p.shift, aux_dt, mrow + v * VEC + 4 * q);
+                scr[it][q] = ld_raw4(p.scale, aux_dt, mrow + v * VEC + 4 * q);
+            }
+        }
+        __syncwarp(__activemask());
     }
     float mean = 0.f;
     if (kLayerNorm) {
@@ -194,7 +243,6 @@ __global__ void __launch_bounds__(256) norm_kernel(const dimsum_norm_modulate_pa
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
     const float rstd = rsqrtf(ss / (float)p.channels + p.eps);
     const float *w = reinterpret_cast<const float *>(p.weight);
-    const int64_t mrow = (warp / p.rows_per_batch) * p.vec_row_stride;
     const int64_t yrow = (int64_t)warp * p.y_row_stride;
 #pragma unroll
     for (int it = 0; it < kMaxIter; ++it) {
@@ -207,12 +255,15 @@ __global__ void __launch_bounds__(256) norm_kernel(const dimsum_norm_modulate_pa
 #pragma unroll
                 for (int i = 0; i < VEC; ++i) o[i] *= w[v * VEC + i];
             }
-            if (p.scale != nullptr) {
-                float sh[VEC], sc[VEC];
-                ld_rt<VEC>(p.shift, (int)p.aux_dtype, mrow + v * VEC, sh);
-                ld_rt<VEC>(p.scale, (int)p.aux_dtype, mrow + v * VEC, sc);
+            if (mod) {
 #pragma unroll
-                for (int i = 0; i < VEC; ++i) o[i] = fmaf(o[i], 1.f + sc[i], sh[i]);
+                for (int q = 0; q < Q; ++q) {
+                    float sh[4], sc[4];
+                    cvt_raw4(shr[it][q], aux_dt, sh);
+                    cvt_raw4(scr[it][q], aux_dt, sc);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) o[4 * q + i] = fmaf(o[4 * q + i], 1.f + sc[i], sh[i]);
+                }
             }
             st_rt<VEC>(p.y, (int)p.y_dtype, yrow + v * VEC, o);
         }

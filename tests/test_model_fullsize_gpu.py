@@ -169,3 +169,32 @@ def test_recorded_forward_and_backward_match_oracle(mode):
     assert total <= tol, total
     # every trainable parameter that the oracle gives a gradient also got one here
     assert all(n in ours for n, v in leaves.items() if v.grad is not None and "cond_proj" not in n)
+
+
+@pytest.mark.parametrize("shadows", [False, True])
+def test_bf16_sampling_forward_matches_oracle_under_autocast(shadows):
+    """The `--dtype bf16` sampling path: eval forward and forward_with_cfg under no_grad + bf16 autocast (glue kernels emitting
+    the GEMM dtype, SiLU(c) cast once, optionally the bf16 weight shadows) against the oracle under the same autocast."""
+    from dimsum_b200 import amp
+    from dimsum_b200.models_dim import DiM
+    from oracle import ref_model
+    raw, sd = _toy()
+    m = DiM(img_resolution=int(raw["cfg/res"]), in_channels=4, hidden_size=int(raw["cfg/hidden"]), depth=int(raw["cfg/depth"]),
+            num_classes=10, label_dropout=0.1, use_attn_every_k_layers=4)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    sh = amp.Bf16Shadows(m) if shadows else None
+    x, t, y = (torch.from_numpy(raw[f"in/{k}"]).cuda() for k in ("x", "t", "y"))
+    leaves = {k: v.cuda() for k, v in sd.items()}
+    try:
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            out = m(x, t, y)
+            cfg = m.forward_with_cfg(torch.cat([x, x]), torch.cat([t, t]), torch.cat([y, torch.full_like(y, 10)]), cfg_scale=4.0)
+            want = ref_model.dim_forward_oracle(leaves, x, t, y)
+    finally:
+        if sh is not None:
+            sh.detach()
+    e = rel_err(out, want)
+    print(f"bf16 sampling forward (shadows={shadows}) rel err vs oracle under autocast: {e:.3e}")
+    assert e <= 2e-2, e
+    assert rel_err(cfg, torch.from_numpy(raw["out/cfg4"]).cuda()) <= 5e-2
