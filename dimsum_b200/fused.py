@@ -1,9 +1,10 @@
-"""Inference-time fused glue around the mixer: adaLN modulate, gated residual (both with the token order folded into the
-row index) and residual-add + RMSNorm.  Reference: `modulate` dimsum/models_dim.py:34-35, the gated residuals
-:1510-1512 / :686-689, the transpose / flip copies :1498-1524, and the Triton `rms_norm_fn`
-(mamba/mamba_ssm/ops/triton/layernorm.py:460).  One coalesced pass each; no permuted copy is materialised.
-The raw kernels have no autograd; `modulate_fn`, `gate_residual_fn` and `gelu_mul_fn` at the end of the file wrap them in
-autograd Functions (backward = the same streaming kernels plus `dimsum_token_colsum` / `dimsum_gelu_mul_bwd`) for training.
+"""Fused glue around the mixer: adaLN modulate, gated residual (both with the token order folded into the row index),
+residual-add + RMSNorm / LayerNorm (+ modulate), GatedMLP activation, CFG + Euler update.  Reference: `modulate`
+dimsum/models_dim.py:34-35, the gated residuals :1510-1512 / :686-689, the transpose / flip copies :1498-1524, and the Triton
+`rms_norm_fn` (mamba/mamba_ssm/ops/triton/layernorm.py:460).  One coalesced pass each; no permuted copy is materialised.
+The raw kernels have no autograd; `modulate_fn`, `gate_residual_fn`, `add_rmsnorm_fn` and `gelu_mul_fn` at the end of the file
+wrap them in autograd Functions for the recorded (training) pass: the backward is the same streaming kernels -- through the
+inverse order table where the forward used one -- plus `dimsum_token_colsum`, `dimsum_gelu_mul_bwd`, `dimsum_add_rmsnorm_bwd`.
 """
 import torch
 
