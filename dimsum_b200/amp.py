@@ -16,15 +16,18 @@ import torch.nn.functional as F
 
 
 def shadow_of(param):
-    """bf16 shadow of a master parameter when one is attached and autocast to bf16 is on -- else None.  A shadow that is
-    older than its master (the optimizer stepped without `Bf16Shadows.refresh()`) is brought up to date on the spot, which
-    costs the cast autocast would have done."""
-    if param is None or not torch.is_autocast_enabled():
+    """bf16 shadow of a master parameter when one is attached and autocast to bf16 is on for its device -- else None.  A shadow
+    that is older than its master (the optimizer stepped without `Bf16Shadows.refresh()`) is brought up to date on the spot,
+    which costs the cast autocast would have done."""
+    if param is None:
         return None
     sh = getattr(param, "_dimsum_bf16", None)
-    if (sh is None or torch.get_autocast_dtype("cuda") != sh.dtype or sh.device != param.device
+    if sh is None:
+        return None
+    dev = param.device.type
+    if (not torch.is_autocast_enabled(dev) or torch.get_autocast_dtype(dev) != sh.dtype or sh.device != param.device
             or param.dtype != torch.float32 or sh.shape != param.shape):
-        return None                                   # the master was moved / recast / resized after the shadow was attached
+        return None                                   # no autocast, or the master was moved / recast / resized since
     if param._dimsum_bf16_version != param._version:
         sh.copy_(param.detach())
         param._dimsum_bf16_version = param._version
@@ -42,7 +45,7 @@ class Bf16Shadows:
             if not isinstance(mod, nn.Linear):
                 continue
             for prm in (mod.weight, mod.bias):
-                if prm is None or id(prm) in seen or prm.dtype != torch.float32 or not prm.is_cuda:
+                if prm is None or id(prm) in seen or prm.dtype != torch.float32:
                     continue
                 seen.add(id(prm))
                 prm._dimsum_bf16 = torch.empty(prm.shape, device=prm.device, dtype=dtype)
